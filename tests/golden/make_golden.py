@@ -1,0 +1,183 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/ref_driver).
+
+Run in the build container (needs /root/reference to have been compiled by
+`make -C oracle/ref`):   python tests/golden/make_golden.py
+The fixtures are committed; the GPU box and CI never run this script.
+
+Each fixture pins one aspect of the hot path against the reference's own objects:
+  geom_<lattice>.npz      neighbour table, colours, sector/colour sets (create_sites / create_set)
+  half_<model>_<lattice>_T<t>.npz   injected-uniform colour half-sweeps, one after another
+  sets_<model>_<lattice>.npz        one iterate_rejection pass over sector->colour sets, injected
+  strict_<model>_<lattice>_T<t>.npz `sweep color/strict` multi-sweep run (per-site Park-Miller)
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+IM = 2147483647
+
+DIM = {"sq/4n": 2, "sq/8n": 2, "tri": 2, "sc/6n": 3, "sc/26n": 3}
+NBASIS = {"sq/4n": 1, "sq/8n": 1, "tri": 2, "sc/6n": 1, "sc/26n": 1}
+NCOLORS = {"sq/4n": 2, "sq/8n": 4, "tri": 4, "sc/6n": 2, "sc/26n": 8}
+DT_SWEEP = {"ising": lambda q, mn: 0.5, "potts": lambda q, mn: 1.0 / q,
+            "potts/pin": lambda q, mn: 1.0 / q, "potts/neighonly": lambda q, mn: 1.0 / mn}
+MAXNEIGH = {"sq/4n": 4, "sq/8n": 8, "tri": 6, "sc/6n": 6, "sc/26n": 26}
+
+
+def tag(s):
+    return s.replace("/", "_")
+
+
+def header(model, q, lattice, n, seed=12345):
+    nx, ny, nz = n
+    app = "ising" if model == "ising" else "%s %d" % (model, q)
+    zreg = "0 %d" % nz if DIM[lattice] == 3 else "-0.5 0.5"
+    return ["seed %d" % seed, "app_style %s" % app, "dimension %d" % DIM[lattice],
+            "lattice %s 1.0" % lattice, "region box block 0 %d 0 %d %s" % (nx, ny, zreg),
+            "create_box box", "create_sites box", "set site range 1 %d" % (2 if model == "ising" else q)]
+
+
+def run_driver(lines, tmp):
+    path = os.path.join(tmp, "drv.in")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    out = subprocess.run([DRIVER, path, "-quiet"], cwd=tmp, capture_output=True, text=True)
+    if out.returncode != 0 or "ERROR" in out.stdout:
+        raise RuntimeError("ref_driver failed:\n" + out.stdout + out.stderr)
+    return out.stdout
+
+
+def ints(tmp, name):
+    return np.fromfile(os.path.join(tmp, name), dtype=np.int32)
+
+
+def nsites(lattice, n):
+    return n[0] * n[1] * (n[2] if DIM[lattice] == 3 else 1) * NBASIS[lattice]
+
+
+def gen_geom(lattice, n):
+    with tempfile.TemporaryDirectory() as tmp:
+        lines = header("potts", 7, lattice, n) + ["sweep color", "sector yes", "temperature 0.5", "run 0.0",
+                                                  "@neigh neigh.bin", "@colors colors.bin", "@sets sets.bin"]
+        run_driver(lines, tmp)
+        ng = ints(tmp, "neigh.bin")
+        nlocal, maxneigh = int(ng[0]), int(ng[1])
+        neigh = ng[2:].reshape(nlocal, maxneigh)
+        colors = ints(tmp, "colors.bin")
+        sets = ints(tmp, "sets.bin")
+    np.savez_compressed(os.path.join(HERE, "geom_%s.npz" % tag(lattice)), n=np.array(n, dtype=np.int32),
+                        neigh=neigh, colors=colors, sets=sets)
+
+
+def random_spins(rng, model, q, ns, pinfrac=0.0, blocky=False):
+    hi = 2 if model == "ising" else q
+    s = rng.integers(1, hi + 1, size=ns, dtype=np.int32)
+    if blocky:  # long runs of equal spins so that neighonly meets few/zero candidates
+        s = np.repeat(rng.integers(1, hi + 1, size=(ns + 15) // 16, dtype=np.int32), 16)[:ns].copy()
+    if pinfrac > 0:
+        s[rng.random(ns) < pinfrac] = q + 1
+    return s
+
+
+def gen_half(model, q, lattice, n, T, rng, blocky=False):
+    ns = nsites(lattice, n)
+    nc = NCOLORS[lattice]
+    with tempfile.TemporaryDirectory() as tmp:
+        spins0 = random_spins(rng, model, q, ns, 0.08 if model == "potts/pin" else 0.0, blocky)
+        spins0.tofile(os.path.join(tmp, "s0.bin"))
+        ks = rng.integers(1, IM - 1, size=(nc, ns), dtype=np.int32)
+        # force a few extreme uniforms (first/last admissible Park-Miller states)
+        ks[:, 0] = 1
+        ks[:, -1] = IM - 1
+        lines = header(model, q, lattice, n) + ["sweep color", "sector no", "temperature %r" % T, "run 0.0",
+                                                "@load s0.bin"]
+        for c in range(nc):
+            ks[c].tofile(os.path.join(tmp, "k%d.bin" % c))
+            lines += ["@halfsweep %d k%d.bin" % (c + 1, c), "@save s%d.bin" % (c + 1)]
+        lines += ["@energy"]
+        out = run_driver(lines, tmp)
+        after = np.stack([ints(tmp, "s%d.bin" % (c + 1)) for c in range(nc)])
+        energy = float([l for l in out.splitlines() if l.startswith("energy")][-1].split()[1])
+    name = "half_%s_%s_T%s%s.npz" % (tag(model), tag(lattice), str(T).replace(".", "p"), "_blocky" if blocky else "")
+    np.savez_compressed(os.path.join(HERE, name), n=np.array(n, dtype=np.int32), q=q, T=T, spins0=spins0, k=ks,
+                        after=after, energy=energy)
+
+
+def gen_sets(model, q, lattice, n, T, rng):
+    """sector yes + sweep color: one pass over the sets in iterate_rejection order."""
+    ns = nsites(lattice, n)
+    with tempfile.TemporaryDirectory() as tmp:
+        spins0 = random_spins(rng, model, q, ns)
+        spins0.tofile(os.path.join(tmp, "s0.bin"))
+        k = rng.integers(1, IM - 1, size=ns, dtype=np.int32)
+        k.tofile(os.path.join(tmp, "k.bin"))
+        lines = header(model, q, lattice, n) + ["sweep color", "sector yes", "temperature %r" % T, "run 0.0",
+                                                "@load s0.bin", "@setsweep k.bin", "@save s1.bin"]
+        run_driver(lines, tmp)
+        after = ints(tmp, "s1.bin")
+    np.savez_compressed(os.path.join(HERE, "sets_%s_%s.npz" % (tag(model), tag(lattice))),
+                        n=np.array(n, dtype=np.int32), q=q, T=T, spins0=spins0, k=k, after=after)
+
+
+def gen_strict(model, q, lattice, n, T, nsweeps, rng):
+    ns = nsites(lattice, n)
+    dt = DT_SWEEP[model](q, MAXNEIGH[lattice])
+    with tempfile.TemporaryDirectory() as tmp:
+        spins0 = random_spins(rng, model, q, ns, 0.05 if model == "potts/pin" else 0.0)
+        spins0.tofile(os.path.join(tmp, "s0.bin"))
+        lines = header(model, q, lattice, n, seed=777) + [
+            "sweep color/strict", "sector no", "temperature %r" % T, "run 0.0", "@load s0.bin",
+            "@siteseeds seeds0.bin", "run %.17g" % (dt * (nsweeps - 0.5)), "@save s1.bin",
+            "@siteseeds seeds1.bin", "@counters", "@energy"]
+        out = run_driver(lines, tmp)
+        seeds0, seeds1, after = ints(tmp, "seeds0.bin"), ints(tmp, "seeds1.bin"), ints(tmp, "s1.bin")
+        cnt = [l for l in out.splitlines() if l.startswith("counters")][-1].split()
+        energy = float([l for l in out.splitlines() if l.startswith("energy")][-1].split()[1])
+        assert int(cnt[3]) == nsweeps, cnt
+    name = "strict_%s_%s_T%s.npz" % (tag(model), tag(lattice), str(T).replace(".", "p"))
+    np.savez_compressed(os.path.join(HERE, name), n=np.array(n, dtype=np.int32), q=q, T=T, nsweeps=nsweeps,
+                        spins0=spins0, seeds0=seeds0, seeds1=seeds1, after=after, naccept=int(cnt[1]),
+                        nattempt=int(cnt[2]), energy=energy, master_seed=777)
+
+
+def main():
+    if not os.path.exists(DRIVER):
+        sys.exit("build the reference first: make -C oracle/ref")
+    rng = np.random.default_rng(20261017)
+    sizes = {"sq/4n": (8, 6, 1), "sq/8n": (6, 8, 1), "tri": (6, 4, 1), "sc/6n": (4, 6, 4), "sc/26n": (6, 4, 4)}
+    for lat, n in sizes.items():
+        gen_geom(lat, n)
+    big = {"sq/4n": (16, 12, 1), "sq/8n": (12, 10, 1), "tri": (8, 10, 1), "sc/6n": (8, 6, 6), "sc/26n": (8, 6, 10)}
+    for T in (0.0, 1.0):
+        gen_half("ising", 2, "sq/4n", big["sq/4n"], T, rng)
+        for lat in big:
+            gen_half("potts", 5, lat, big[lat], T, rng)
+        gen_half("potts/neighonly", 6, "sc/26n", big["sc/26n"], T, rng)
+        gen_half("potts/neighonly", 4, "tri", big["tri"], T, rng)
+        gen_half("potts/pin", 5, "sc/26n", big["sc/26n"], T, rng)
+    gen_half("ising", 2, "sc/6n", big["sc/6n"], 2.2, rng)
+    gen_half("ising", 2, "sq/8n", big["sq/8n"], 3.0, rng)
+    gen_half("potts/neighonly", 10000, "sc/26n", big["sc/26n"], 0.5, rng)
+    gen_half("potts/neighonly", 3, "sc/26n", big["sc/26n"], 0.7, rng, blocky=True)
+    gen_half("potts/neighonly", 3, "sq/4n", big["sq/4n"], 0.0, rng, blocky=True)
+    gen_half("potts/pin", 50, "sq/8n", big["sq/8n"], 0.9, rng)
+    gen_sets("potts", 5, "sc/26n", (8, 6, 10), 0.8, rng)
+    gen_sets("ising", 2, "sq/4n", (10, 14, 1), 1.5, rng)
+    gen_sets("potts", 4, "tri", (6, 10, 1), 0.6, rng)
+    gen_strict("ising", 2, "sq/4n", (16, 12, 1), 1.1346, 5, rng)
+    gen_strict("potts", 7, "sc/26n", (6, 6, 8), 0.9, 4, rng)
+    gen_strict("potts/neighonly", 9, "sc/26n", (6, 6, 8), 0.5, 4, rng)
+    gen_strict("potts/pin", 6, "sc/26n", (6, 6, 8), 1.2, 4, rng)
+    gen_strict("potts", 12, "tri", (8, 8, 1), 0.0, 6, rng)
+    print("wrote", len([f for f in os.listdir(HERE) if f.endswith(".npz")]), "fixtures")
+
+
+if __name__ == "__main__":
+    main()
