@@ -1,0 +1,135 @@
+/* libspparks_cuda — C ABI of the B200-native rejection-KMC colour sweep for SPPARKS lattices.
+ *
+ * This is the drop-in boundary.  The reference has no FFI for this path: the
+ * "binding" is a C++ app-style plugin (plugin/app_*_cuda.{h,cpp}, registered through
+ * style_app.h exactly like src/app_potts_neighonly.h:18-42) whose init_app()/iterate_rejection()
+ * call the functions below instead of running AppLattice::sweep_*() on the host.  Each entry
+ * point cites the reference interface it replaces (paths relative to the SPPARKS tree).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, non-zero on error, and
+ *     spk_cuda_last_error() returns the message (the plugin forwards it to error->one(),
+ *     src/error.cpp:105-115).
+ *   - host pointers are only read/written during the call; device memory belongs to the handle.
+ *   - sites are in reference order: id-1 = ((k*ny + j)*nx + i)*nbasis + m
+ *     (src/create_sites.cpp:344-350); colours are 1-based as Lattice::id2color returns them
+ *     (src/lattice.cpp:234-283).
+ *   - a slab handle (nranks > 1) owns the cells  [slab_lo, slab_hi)  of the LAST dimension
+ *     (z in 3-D = `processors 1 1 N`, y in 2-D = `processors 1 N 1`, src/domain.cpp:204-328) and
+ *     one ghost plane on each side (delpropensity = 1, src/app_potts.cpp:35).
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef SPPARKS_CUDA_H
+#define SPPARKS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPK_CUDA_ABI_VERSION 1
+
+/* app_style on the path: AppIsing (src/app_ising.cpp:104-136), AppPotts (src/app_potts.cpp:112-146),
+ * AppPottsNeighOnly (src/app_potts_neighonly.cpp:71-117), AppPottsPin (src/app_potts_pin.cpp:93-131) */
+enum { SPK_ISING = 0, SPK_POTTS = 1, SPK_POTTS_NEIGHONLY = 2, SPK_POTTS_PIN = 3 };
+/* lattice styles with the reference's enum values (src/lattice.cpp:32-33) */
+enum { SPK_SQ_4N = 2, SPK_SQ_8N = 3, SPK_TRI = 4, SPK_SC_6N = 5, SPK_SC_26N = 6 };
+
+typedef struct {
+  int32_t model;        /* SPK_ISING ... */
+  int32_t lattice;      /* SPK_SQ_4N ... */
+  int32_t nx, ny, nz;   /* GLOBAL extents in unit cells, all even (src/lattice.cpp:187-228); nz = 1 in 2-D */
+  int32_t nspins;       /* Q of `app_style potts Q`; ignored for ising */
+  double temperature;   /* `temperature` command (src/app_lattice.cpp:889-894) */
+  uint64_t seed;        /* key of the counter-based Philox stream (replaces ranapp, src/app_lattice.cpp:274-278) */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t rank, nranks; /* slab index / number of slabs along the last dimension; 0,1 = whole lattice */
+} spk_cuda_desc;
+
+typedef struct spk_cuda_handle spk_cuda_handle;
+
+const char *spk_cuda_last_error(void);
+int spk_cuda_abi_version(void);
+int spk_cuda_device_count(int *count);
+
+/* lifetime: AppLattice::init()/init_app() (src/app_lattice.cpp:133-327) creates, ~App destroys */
+int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out);
+int spk_cuda_destroy(spk_cuda_handle *h);
+
+/* geometry queries (Lattice::ncolors src/lattice.cpp:187-228; CreateSites maxneigh src/create_sites.cpp:535-540) */
+int spk_cuda_ncolors(int lattice);
+int spk_cuda_maxneigh(int lattice);
+int spk_cuda_nbasis(int lattice);
+int64_t spk_cuda_nlocal(const spk_cuda_handle *h);  /* owned sites of this slab */
+int64_t spk_cuda_nglobal(const spk_cuda_handle *h);
+
+/* spin = iarray[0] (src/app_potts.cpp:68-71): host <-> device, n = nlocal owned sites */
+int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n);
+int spk_cuda_download_spins(spk_cuda_handle *h, int32_t *host, int64_t n);
+/* `temperature` (src/app_lattice.cpp:889-894): rebuilds the exp() acceptance tables on the host */
+int spk_cuda_set_temperature(spk_cuda_handle *h, double temperature);
+
+/* device-side synthetic initialisation for lattices too large for the host path
+ * (distribution of `set site range lo hi`, src/set.cpp:582-627, and of `pin f 0 0`,
+ * src/app_potts_pin.cpp:262-283; NOT the reference's random stream) */
+int spk_cuda_randomize(spk_cuda_handle *h, uint64_t seed, int32_t lo, int32_t hi);
+int spk_cuda_pin_random(spk_cuda_handle *h, uint64_t seed, double fraction);
+
+/* One colour set = one kernel: replaces (this->*sweep)(set.nlocal,set.site2i) x nloop
+ * (src/app_lattice.cpp:674-691) for the set {sites of `color` inside `box`}.
+ * box = {ilo,ihi,jlo,jhi,klo,khi} half-open GLOBAL cell ranges = the sector of create_set()
+ * (src/app_lattice.cpp:969-984), or NULL for the whole lattice.  Randoms: Philox4x32-10 keyed
+ * on (seed; global site, sweep, colour, iloop).  Ghost planes must be current (spk_cuda_halo_exchange). */
+int spk_cuda_sweep_color(spk_cuda_handle *h, uint32_t sweep, int color, const int32_t *box, int nloop);
+
+/* Parity mode: the same set with the two uniforms of site_event_rejection INJECTED per owned
+ * site (host arrays of nlocal doubles: u1 = first random->uniform(), u2 = second).  Uses the
+ * reference's double-precision formulas and a host-computed exp() table. */
+int spk_cuda_sweep_color_injected(spk_cuda_handle *h, int color, const int32_t *box,
+                                  const double *u1, const double *u2);
+
+/* Parity mode `sweep color/strict`: per-site Park-Miller streams, sweep_nomask_strict
+ * (src/app_lattice.cpp:287-295, 796-805; RandomPark::uniform src/random_park.cpp:79-86) */
+int spk_cuda_set_siteseeds(spk_cuda_handle *h, const int32_t *seeds, int64_t n);
+int spk_cuda_get_siteseeds(spk_cuda_handle *h, int32_t *seeds, int64_t n);
+int spk_cuda_sweep_color_strict(spk_cuda_handle *h, int color, const int32_t *box, int nloop);
+
+/* nsweeps full sweeps of iterate_rejection with `sweep color`, `sector no`
+ * (src/app_lattice.cpp:646-705): for each sweep, for each colour 1..ncolors: ghost refresh
+ * (comm->all(), src/app_lattice.cpp:650-651) then the colour kernel.  Sweep numbers
+ * first_sweep .. first_sweep+nsweeps-1 key the random stream.  Bit-identical to calling
+ * spk_cuda_halo_exchange + spk_cuda_sweep_color per colour, but free to fuse colours. */
+int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps);
+
+/* AppLattice::stats (src/app_lattice.cpp:917-934): cumulative accepted / attempted events of
+ * this slab since create or the last reset (the caller sums over ranks, as MPI_Allreduce does) */
+int spk_cuda_counters(spk_cuda_handle *h, int64_t *naccept, int64_t *nattempt);
+int spk_cuda_reset_counters(spk_cuda_handle *h);
+
+/* diag_style energy (src/diag_energy.cpp:53-66): sum of site_energy over owned sites */
+int spk_cuda_energy(spk_cuda_handle *h, double *energy);
+
+/* multi-GPU: one process per GPU; rank 0 creates the id, the host broadcasts it (MPI_Bcast in
+ * the plugin, torch.distributed in bench.py), every rank joins.  Replaces CommLattice::init
+ * (src/comm_lattice.cpp:74-135). */
+#define SPK_CUDA_COMM_ID_BYTES 128
+int spk_cuda_comm_id(char id[SPK_CUDA_COMM_ID_BYTES]);
+int spk_cuda_comm_init(spk_cuda_handle *h, const char id[SPK_CUDA_COMM_ID_BYTES]);
+/* CommLattice::all() -> perform_swap_site (src/comm_lattice.cpp:137-143, 912-946): refresh both
+ * ghost planes from the ring neighbours (or from the periodic image when nranks == 1) */
+int spk_cuda_halo_exchange(spk_cuda_handle *h);
+
+/* stream control and device timing (CUDA events recorded on the handle's own stream) */
+int spk_cuda_sync(spk_cuda_handle *h);
+int spk_cuda_timer_start(spk_cuda_handle *h);
+int spk_cuda_timer_stop(spk_cuda_handle *h, float *milliseconds);
+/* number of kernels this handle has launched since create (bench.py's gpu_launches) */
+int spk_cuda_launch_count(spk_cuda_handle *h, int64_t *launches);
+/* raw device pointer to the first owned site (row-major, reference order) for zero-copy hosts */
+int spk_cuda_device_spins(spk_cuda_handle *h, void **dptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,89 @@
+"""ctypes binding of libspparks_cuda (include/spparks_cuda.h).
+
+There is no CPU fallback: if the shared library is missing, or a call fails (e.g. no CUDA
+device), a SpkCudaError is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libspparks_cuda.so")
+
+ISING, POTTS, POTTS_NEIGHONLY, POTTS_PIN = 0, 1, 2, 3
+SQ_4N, SQ_8N, TRI, SC_6N, SC_26N = 2, 3, 4, 5, 6
+COMM_ID_BYTES = 128
+
+# every symbol include/spparks_cuda.h declares (tests check that the library exports them all)
+SYMBOLS = [
+    "spk_cuda_last_error", "spk_cuda_abi_version", "spk_cuda_device_count", "spk_cuda_create",
+    "spk_cuda_destroy", "spk_cuda_ncolors", "spk_cuda_maxneigh", "spk_cuda_nbasis", "spk_cuda_nlocal",
+    "spk_cuda_nglobal", "spk_cuda_upload_spins", "spk_cuda_download_spins", "spk_cuda_set_temperature",
+    "spk_cuda_randomize", "spk_cuda_pin_random", "spk_cuda_sweep_color", "spk_cuda_sweep_color_injected",
+    "spk_cuda_set_siteseeds", "spk_cuda_get_siteseeds", "spk_cuda_sweep_color_strict", "spk_cuda_sweeps",
+    "spk_cuda_counters", "spk_cuda_reset_counters", "spk_cuda_energy", "spk_cuda_comm_id",
+    "spk_cuda_comm_init", "spk_cuda_halo_exchange", "spk_cuda_sync", "spk_cuda_timer_start",
+    "spk_cuda_timer_stop", "spk_cuda_launch_count", "spk_cuda_device_spins",
+]
+
+
+class SpkCudaError(RuntimeError):
+    pass
+
+
+class Desc(C.Structure):
+    _fields_ = [("model", C.c_int32), ("lattice", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32),
+                ("nz", C.c_int32), ("nspins", C.c_int32), ("temperature", C.c_double),
+                ("seed", C.c_uint64), ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load libspparks_cuda.so; fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SpkCudaError("libspparks_cuda.so not built (%s); run `make -C spparks_b200/csrc` or "
+                           "__graft_entry__.build()" % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32p, i64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    dp = C.POINTER(C.c_double)
+    L.spk_cuda_last_error.restype = C.c_char_p
+    L.spk_cuda_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.spk_cuda_create.argtypes = [C.POINTER(Desc), C.POINTER(vp)]
+    L.spk_cuda_destroy.argtypes = [vp]
+    L.spk_cuda_nlocal.restype = C.c_int64
+    L.spk_cuda_nlocal.argtypes = [vp]
+    L.spk_cuda_nglobal.restype = C.c_int64
+    L.spk_cuda_nglobal.argtypes = [vp]
+    L.spk_cuda_upload_spins.argtypes = [vp, vp, C.c_int64]
+    L.spk_cuda_download_spins.argtypes = [vp, vp, C.c_int64]
+    L.spk_cuda_set_temperature.argtypes = [vp, C.c_double]
+    L.spk_cuda_randomize.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32]
+    L.spk_cuda_pin_random.argtypes = [vp, C.c_uint64, C.c_double]
+    L.spk_cuda_sweep_color.argtypes = [vp, C.c_uint32, C.c_int, i32p, C.c_int]
+    L.spk_cuda_sweep_color_injected.argtypes = [vp, C.c_int, i32p, dp, dp]
+    L.spk_cuda_set_siteseeds.argtypes = [vp, vp, C.c_int64]
+    L.spk_cuda_get_siteseeds.argtypes = [vp, vp, C.c_int64]
+    L.spk_cuda_sweep_color_strict.argtypes = [vp, C.c_int, i32p, C.c_int]
+    L.spk_cuda_sweeps.argtypes = [vp, C.c_uint32, C.c_int]
+    L.spk_cuda_counters.argtypes = [vp, i64p, i64p]
+    L.spk_cuda_reset_counters.argtypes = [vp]
+    L.spk_cuda_energy.argtypes = [vp, dp]
+    L.spk_cuda_comm_id.argtypes = [C.c_char_p]
+    L.spk_cuda_comm_init.argtypes = [vp, C.c_char_p]
+    L.spk_cuda_halo_exchange.argtypes = [vp]
+    L.spk_cuda_sync.argtypes = [vp]
+    L.spk_cuda_timer_start.argtypes = [vp]
+    L.spk_cuda_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.spk_cuda_launch_count.argtypes = [vp, i64p]
+    L.spk_cuda_device_spins.argtypes = [vp, C.POINTER(vp)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise SpkCudaError(load().spk_cuda_last_error().decode())

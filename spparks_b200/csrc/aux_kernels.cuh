@@ -1,0 +1,89 @@
+// Device-side helpers around the sweep: synthetic initialisation, pinning, energy reduction.
+#pragma once
+#include "event.cuh"
+
+namespace spk {
+
+// `set site range lo hi` distribution (src/set.cpp:617-627) from a counter-based stream keyed
+// on the GLOBAL site index: value = lo + floor(range * w/2^32).
+__global__ void randomize_kernel(int32_t *spin, long long n, long long goff, unsigned long long seed, int lo,
+                                 uint32_t range) {
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n; s += (long long)gridDim.x * blockDim.x) {
+    unsigned long long gs = (unsigned long long)(s + goff);
+    uint2 w = philox4x32_10_w01((uint32_t)gs, (uint32_t)(gs >> 32), 0x5e7517e5u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    spin[s] = lo + (int)__umulhi(range, w.x);
+  }
+}
+
+// Bernoulli(fraction) pinning, the large-lattice stand-in for `pin f 0 0`
+// (src/app_potts_pin.cpp:262-283 draws ndesired random sites; here each site is pinned
+// independently with the same probability).  Pinned value = Q+1 (src/app_potts_pin.cpp:271).
+__global__ void pin_kernel(int32_t *spin, long long n, long long goff, unsigned long long seed, uint32_t thr,
+                           int pinned) {
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n; s += (long long)gridDim.x * blockDim.x) {
+    unsigned long long gs = (unsigned long long)(s + goff);
+    uint2 w = philox4x32_10_w01((uint32_t)gs, (uint32_t)(gs >> 32), 0x9199ed51u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    if (w.x < thr) spin[s] = pinned;
+  }
+}
+
+// diag_style energy (src/diag_energy.cpp:53-66): sum over owned sites of site_energy(i)
+template <int LAT>
+__global__ void __launch_bounds__(256) energy_kernel(const int32_t *__restrict__ spin, Geo g, unsigned long long *out) {
+  using L = Lat<LAT>;
+  constexpr int NN = L::NN, NB = L::NB;
+  const long long sy = (long long)g.X * NB, sz = sy * g.Y;
+  const long long ncell = (long long)g.X * g.Y * g.Z;
+  unsigned int e = 0;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % g.X);
+    const int j = (int)((c / g.X) % g.Y);
+    const int k = (int)(c / ((long long)g.X * g.Y));
+    const int xi[3] = {i == 0 ? g.X - 1 : i - 1, i, i == g.X - 1 ? 0 : i + 1};
+    int yj[3], zk[3];
+    if (L::DIM == 2) {
+      yj[0] = j == 0 ? g.lo_wrap : j - 1; yj[1] = j; yj[2] = j == g.Y - 1 ? g.hi_wrap : j + 1;
+      zk[0] = zk[1] = zk[2] = 0;
+    } else {
+      yj[0] = j == 0 ? g.Y - 1 : j - 1; yj[1] = j; yj[2] = j == g.Y - 1 ? 0 : j + 1;
+      zk[0] = k == 0 ? g.lo_wrap : k - 1; zk[1] = k; zk[2] = k == g.Z - 1 ? g.hi_wrap : k + 1;
+    }
+#pragma unroll
+    for (int m = 0; m < NB; m++) {
+      const int me = spin[zk[1] * sz + yj[1] * sy + (long long)i * NB + m];
+#pragma unroll
+      for (int n = 0; n < NN; n++) {
+        const Off o = L::off(m, n);
+        e += (spin[zk[o.dz + 1] * sz + yj[o.dy + 1] * sy + (long long)xi[o.dx + 1] * NB + o.m] != me);
+      }
+    }
+  }
+  e = __reduce_add_sync(0xffffffffu, e);
+  __shared__ unsigned int part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += part[w];
+    if (t) atomicAdd(out, t);
+  }
+}
+
+inline int launch_energy(int lattice, cudaStream_t st, const int32_t *spin, const Geo &g, unsigned long long *out,
+                         int64_t *launches) {
+  const long long ncell = (long long)g.X * g.Y * g.Z;
+  long long want = (ncell + 255) / 256;
+  const int grid = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
+  switch (lattice) {
+    case SPK_SQ_4N: energy_kernel<SPK_SQ_4N><<<grid, 256, 0, st>>>(spin, g, out); break;
+    case SPK_SQ_8N: energy_kernel<SPK_SQ_8N><<<grid, 256, 0, st>>>(spin, g, out); break;
+    case SPK_TRI: energy_kernel<SPK_TRI><<<grid, 256, 0, st>>>(spin, g, out); break;
+    case SPK_SC_6N: energy_kernel<SPK_SC_6N><<<grid, 256, 0, st>>>(spin, g, out); break;
+    case SPK_SC_26N: energy_kernel<SPK_SC_26N><<<grid, 256, 0, st>>>(spin, g, out); break;
+    default: return 1;
+  }
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace spk

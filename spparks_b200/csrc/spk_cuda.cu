@@ -1,0 +1,567 @@
+// libspparks_cuda: C ABI (include/spparks_cuda.h) over the sm_100a colour-sweep kernels.
+// No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound lazily with dlopen (see NcclApi)
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/spparks_cuda.h"
+#include "aux_kernels.cuh"
+#include "sweep_generic.cuh"
+#include "sweep_tiled.cuh"
+
+using namespace spk;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CU(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+// NCCL is bound at the first multi-GPU call, not at link time: a host process (PyTorch, an MPI
+// SPPARKS) may already carry its own libnccl.so.2 and two copies must not be mixed.  dlopen by
+// SONAME returns the copy that is already loaded, if any.  SPK_CUDA_NCCL_LIB overrides the path.
+struct NcclApi {
+  void *dl = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+int nccl_bind() {
+  if (g_nccl.dl) return 0;
+  const char *override_path = getenv("SPK_CUDA_NCCL_LIB");
+  void *dl = dlopen(override_path ? override_path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!dl) return fail("cannot load NCCL: %s", dlerror());
+#define BIND(name)                                                          \
+  *(void **)(&g_nccl.name) = dlsym(dl, "nccl" #name);                       \
+  if (!g_nccl.name) return fail("NCCL symbol nccl" #name " not found")
+  BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(GroupStart); BIND(GroupEnd);
+  BIND(Send); BIND(Recv); BIND(GetErrorString);
+#undef BIND
+  g_nccl.dl = dl;
+  return 0;
+}
+
+#define NC(call)                                                                        \
+  do {                                                                                  \
+    ncclResult_t r_ = (call);                                                           \
+    if (r_ != ncclSuccess) return fail("%s: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+
+int lat_dim(int lat) { return (lat == SPK_SC_6N || lat == SPK_SC_26N) ? 3 : 2; }
+
+}  // namespace
+
+struct spk_cuda_handle {
+  spk_cuda_desc d;
+  int dim, nb, nn, nc;
+  Geo g;
+  int64_t nlocal, nglobal, plane;  // plane = elements of one plane (3-D) / row (2-D) of the slab dimension
+  int nslab;                       // local extent along the slab dimension
+  int32_t *base = nullptr;         // allocation incl. ghost planes
+  int32_t *spin = nullptr;         // first owned site
+  double *u1 = nullptr, *u2 = nullptr;
+  int32_t *seeds = nullptr;
+  unsigned long long *naccept = nullptr, *escratch = nullptr;
+  int64_t nattempt = 0, launches = 0;
+  EventParams ev;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr, ev_halo = nullptr, ev_compute = nullptr;
+  ncclComm_t comm = nullptr;
+  bool tiled = true;  // tuned kernels allowed (SPK_CUDA_FORCE_GENERIC=1 disables, for A/B tests)
+};
+
+namespace {
+
+void build_tables(spk_cuda_handle *h) {
+  // exp((einitial-efinal)*t_inverse) of site_event_rejection (src/app_potts.cpp:130), evaluated
+  // with the host libm for every possible integer dE so that device results are bit-identical
+  EventParams &ev = h->ev;
+  ev.nspins = h->d.model == SPK_ISING ? 2 : h->d.nspins;
+  ev.t_zero = h->d.temperature == 0.0;
+  ev.k0 = (uint32_t)h->d.seed;
+  ev.k1 = (uint32_t)(h->d.seed >> 32);
+  ev.sweep = 0;
+  const double t_inverse = ev.t_zero ? 0.0 : 1.0 / h->d.temperature;
+  for (int dE = 0; dE < 27; dE++) {
+    double p = ev.t_zero ? 0.0 : std::exp((0.0 - (double)dE) * t_inverse);
+    ev.ptab[dE] = p;
+    double t = std::floor(p * 4294967296.0);
+    ev.thr[dE] = t > 4294967295.0 ? 4294967295u : (uint32_t)t;
+  }
+}
+
+// sector box (global cells) -> local cell ranges of this slab; false if empty
+bool local_box(const spk_cuda_handle *h, const int32_t *box, Box &b) {
+  const Geo &g = h->g;
+  int lo[3] = {0, 0, 0}, hi[3] = {g.gX, g.gY, g.gZ};
+  if (box)
+    for (int a = 0; a < 3; a++) {
+      lo[a] = box[2 * a] < 0 ? 0 : box[2 * a];
+      hi[a] = box[2 * a + 1] > hi[a] ? hi[a] : box[2 * a + 1];
+    }
+  const int sd = h->dim - 1;  // slab dimension
+  lo[sd] -= g.g0; hi[sd] -= g.g0;
+  if (lo[sd] < 0) lo[sd] = 0;
+  if (hi[sd] > h->nslab) hi[sd] = h->nslab;
+  b = Box{lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]};
+  return lo[0] < hi[0] && lo[1] < hi[1] && lo[2] < hi[2];
+}
+
+// sites of colour c0 inside the local box (nattempt += nselect, src/app_lattice.cpp:677)
+template <int LAT> int64_t class_count(const spk_cuda_handle *h, const Box &b, int c0) {
+  auto par = [](int lo, int hi, int p) -> int64_t {  // # of x in [lo,hi) with x%2 == p
+    int first = lo + ((lo ^ p) & 1);
+    return first < hi ? (hi - first + 1) / 2 : 0;
+  };
+  const int64_t ni = b.ihi - b.ilo, nj = b.jhi - b.jlo, nk = b.khi - b.klo;
+  if (LAT == SPK_SQ_4N || LAT == SPK_SC_6N) {
+    int64_t n = 0;
+    for (int k = b.klo; k < b.khi; k++)
+      for (int par_j = 0; par_j < 2; par_j++) {
+        int shift = LAT == SPK_SQ_4N ? h->g.g0 : k + h->g.g0;
+        n += par(b.jlo, b.jhi, par_j) * par(b.ilo, b.ihi, (c0 + par_j + shift) & 1);
+      }
+    return n;
+  }
+  if (LAT == SPK_SQ_8N) return par(b.ilo, b.ihi, c0 & 1) * par(b.jlo, b.jhi, (c0 >> 1) & 1);
+  if (LAT == SPK_TRI) return par(b.ilo, b.ihi, (c0 >> 1) & 1) * nj;
+  (void)ni; (void)nk;
+  return par(b.ilo, b.ihi, c0 & 1) * par(b.jlo, b.jhi, (c0 >> 1) & 1) * par(b.klo, b.khi, (c0 >> 2) & 1);
+}
+
+template <int LAT, int MODEL, int RNG>
+int launch_generic(spk_cuda_handle *h, const SweepArgs &a) {
+  const Box &b = a.b;
+  const int half_x = (b.ihi - b.ilo + 1) / 2 + 1;
+  int rows = b.jhi - b.jlo, planes = b.khi - b.klo;
+  if (LAT == SPK_SQ_8N || LAT == SPK_SC_26N) rows = rows / 2 + 1;
+  if (LAT == SPK_SC_26N) planes = planes / 2 + 1;
+  if (Lat<LAT>::DIM == 2) planes = 1;
+  dim3 block(64, 4, 1);
+  dim3 grid((half_x + 63) / 64, (rows + 3) / 4, planes);
+  if (grid.y > 65535 || grid.z > 65535) return fail("lattice too large for the generic kernel grid");
+  sweep_generic_kernel<LAT, MODEL, RNG><<<grid, block, 0, h->stream>>>(a);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int LAT, int MODEL>
+int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
+  SweepArgs a;
+  a.spin = h->spin; a.g = h->g; a.c0 = color - 1; a.nloop = nloop; a.ev = h->ev;
+  a.u1 = h->u1; a.u2 = h->u2; a.seeds = h->seeds; a.naccept = h->naccept;
+  if (!local_box(h, box, a.b)) return 0;
+  h->nattempt += class_count<LAT>(h, a.b, a.c0) * nloop;
+  if (rng == RNG_PHILOX) {
+    if (h->tiled) {
+      int rc = launch_tiled<LAT, MODEL>(h->stream, a, &h->launches);
+      if (rc == 0) return 0;
+      if (rc > 0) return fail("tiled kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    return launch_generic<LAT, MODEL, RNG_PHILOX>(h, a);
+  }
+  if (rng == RNG_INJECTED) return launch_generic<LAT, MODEL, RNG_INJECTED>(h, a);
+  return launch_generic<LAT, MODEL, RNG_STRICT>(h, a);
+}
+
+template <int LAT> int sweep_set_l(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
+  switch (h->d.model) {
+    case SPK_ISING: return sweep_set_lm<LAT, SPK_ISING>(h, rng, color, box, nloop);
+    case SPK_POTTS: return sweep_set_lm<LAT, SPK_POTTS>(h, rng, color, box, nloop);
+    case SPK_POTTS_NEIGHONLY: return sweep_set_lm<LAT, SPK_POTTS_NEIGHONLY>(h, rng, color, box, nloop);
+    case SPK_POTTS_PIN: return sweep_set_lm<LAT, SPK_POTTS_PIN>(h, rng, color, box, nloop);
+  }
+  return fail("unknown model %d", h->d.model);
+}
+
+int sweep_set(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
+  if (!h) return fail("null handle");
+  if (color < 1 || color > h->nc) return fail("colour %d out of range 1..%d", color, h->nc);
+  if (nloop < 1) return fail("nloop must be >= 1");
+  CU(cudaSetDevice(h->d.device));
+  switch (h->d.lattice) {
+    case SPK_SQ_4N: return sweep_set_l<SPK_SQ_4N>(h, rng, color, box, nloop);
+    case SPK_SQ_8N: return sweep_set_l<SPK_SQ_8N>(h, rng, color, box, nloop);
+    case SPK_TRI: return sweep_set_l<SPK_TRI>(h, rng, color, box, nloop);
+    case SPK_SC_6N: return sweep_set_l<SPK_SC_6N>(h, rng, color, box, nloop);
+    case SPK_SC_26N: return sweep_set_l<SPK_SC_26N>(h, rng, color, box, nloop);
+  }
+  return fail("unknown lattice %d", h->d.lattice);
+}
+
+}  // namespace
+
+// ================================================================================== ABI
+
+extern "C" {
+
+const char *spk_cuda_last_error(void) { return g_err.c_str(); }
+int spk_cuda_abi_version(void) { return SPK_CUDA_ABI_VERSION; }
+
+int spk_cuda_device_count(int *count) {
+  if (!count) return fail("null argument");
+  CU(cudaGetDeviceCount(count));
+  return 0;
+}
+
+int spk_cuda_ncolors(int lat) {
+  switch (lat) {
+    case SPK_SQ_4N: case SPK_SC_6N: return 2;
+    case SPK_SQ_8N: case SPK_TRI: return 4;
+    case SPK_SC_26N: return 8;
+  }
+  return 0;
+}
+int spk_cuda_maxneigh(int lat) {
+  switch (lat) {
+    case SPK_SQ_4N: return 4;
+    case SPK_SQ_8N: return 8;
+    case SPK_TRI: case SPK_SC_6N: return 6;
+    case SPK_SC_26N: return 26;
+  }
+  return 0;
+}
+int spk_cuda_nbasis(int lat) { return lat == SPK_TRI ? 2 : (spk_cuda_maxneigh(lat) ? 1 : 0); }
+
+int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
+  if (!desc || !out) return fail("null argument");
+  *out = nullptr;
+  const int nn = spk_cuda_maxneigh(desc->lattice);
+  if (!nn) return fail("unsupported lattice style %d", desc->lattice);
+  if (desc->model < SPK_ISING || desc->model > SPK_POTTS_PIN) return fail("unsupported app model %d", desc->model);
+  const int dim = lat_dim(desc->lattice);
+  const int nz = dim == 3 ? desc->nz : 1;
+  if (desc->nx < 2 || desc->ny < 2 || nz < 1) return fail("lattice extents must be >= 2");
+  // Lattice::ncolors: "Color stencil is incommensurate with lattice size" (src/lattice.cpp:198-221);
+  // tri only needs nx even
+  if (desc->nx % 2 || (desc->lattice != SPK_TRI && desc->ny % 2) || (dim == 3 && nz % 2))
+    return fail("Color stencil is incommensurate with lattice size");
+  if (desc->model != SPK_ISING && desc->nspins <= 0) return fail("Illegal app_style command: nspins must be > 0");
+  if (desc->temperature < 0.0) return fail("temperature must be >= 0");
+  if (desc->nranks < 1 || desc->rank < 0 || desc->rank >= desc->nranks) return fail("bad rank/nranks");
+  const int nslab_g = dim == 3 ? nz : desc->ny;
+  if (nslab_g % desc->nranks || (nslab_g / desc->nranks) % 2 || nslab_g / desc->nranks < 2)
+    return fail("slab dimension %d does not split into %d even slabs", nslab_g, desc->nranks);
+
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (desc->device < 0 || desc->device >= ndev) return fail("CUDA device %d not available (%d visible)", desc->device, ndev);
+  CU(cudaSetDevice(desc->device));
+
+  spk_cuda_handle *h = new spk_cuda_handle;
+  h->d = *desc;
+  h->d.nz = nz;
+  h->dim = dim; h->nn = nn; h->nb = spk_cuda_nbasis(desc->lattice); h->nc = spk_cuda_ncolors(desc->lattice);
+  h->nslab = nslab_g / desc->nranks;
+  Geo &g = h->g;
+  g.gX = desc->nx; g.gY = desc->ny; g.gZ = nz;
+  g.X = desc->nx; g.Y = dim == 3 ? desc->ny : h->nslab; g.Z = dim == 3 ? h->nslab : 1;
+  g.g0 = desc->rank * h->nslab;
+  if (desc->nranks == 1) { g.lo_wrap = h->nslab - 1; g.hi_wrap = 0; }
+  else { g.lo_wrap = -1; g.hi_wrap = h->nslab; }
+  h->plane = dim == 3 ? (int64_t)g.X * g.Y * h->nb : (int64_t)g.X * h->nb;
+  h->nlocal = h->plane * h->nslab;
+  h->nglobal = (int64_t)desc->nx * desc->ny * nz * h->nb;
+  const char *fg = getenv("SPK_CUDA_FORCE_GENERIC");
+  h->tiled = !(fg && fg[0] == '1');
+  build_tables(h);
+
+  auto cleanup = [&](int rc) { spk_cuda_destroy(h); return rc; };
+  const size_t bytes = (size_t)(h->nlocal + 2 * h->plane) * sizeof(int32_t);
+  if (cudaMalloc(&h->base, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return cleanup(fail("cudaMalloc of %zu bytes for the lattice failed", bytes));
+  }
+  h->spin = h->base + h->plane;
+  if (cudaMemset(h->base, 0, bytes) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
+  if (cudaMalloc(&h->naccept, 2 * sizeof(unsigned long long)) != cudaSuccess) return cleanup(fail("cudaMalloc failed"));
+  h->escratch = h->naccept + 1;
+  cudaMemset(h->naccept, 0, 2 * sizeof(unsigned long long));
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->t0) != cudaSuccess || cudaEventCreate(&h->t1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming) != cudaSuccess)
+    return cleanup(fail("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())));
+  *out = h;
+  return 0;
+}
+
+int spk_cuda_destroy(spk_cuda_handle *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->d.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  cudaFree(h->base); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
+  if (h->t0) cudaEventDestroy(h->t0);
+  if (h->t1) cudaEventDestroy(h->t1);
+  if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+  if (h->ev_compute) cudaEventDestroy(h->ev_compute);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  delete h;
+  return 0;
+}
+
+int64_t spk_cuda_nlocal(const spk_cuda_handle *h) { return h ? h->nlocal : 0; }
+int64_t spk_cuda_nglobal(const spk_cuda_handle *h) { return h ? h->nglobal : 0; }
+
+int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n) {
+  if (!h || !host) return fail("null argument");
+  if (n != h->nlocal) return fail("upload of %lld sites, slab owns %lld", (long long)n, (long long)h->nlocal);
+  CU(cudaSetDevice(h->d.device));
+  CU(cudaMemcpyAsync(h->spin, host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int spk_cuda_download_spins(spk_cuda_handle *h, int32_t *host, int64_t n) {
+  if (!h || !host) return fail("null argument");
+  if (n != h->nlocal) return fail("download of %lld sites, slab owns %lld", (long long)n, (long long)h->nlocal);
+  CU(cudaSetDevice(h->d.device));
+  CU(cudaMemcpyAsync(host, h->spin, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int spk_cuda_set_temperature(spk_cuda_handle *h, double temperature) {
+  if (!h) return fail("null handle");
+  if (temperature < 0.0) return fail("temperature must be >= 0");
+  h->d.temperature = temperature;
+  const uint32_t sweep = h->ev.sweep;
+  build_tables(h);
+  h->ev.sweep = sweep;
+  return 0;
+}
+
+int spk_cuda_randomize(spk_cuda_handle *h, uint64_t seed, int32_t lo, int32_t hi) {
+  if (!h) return fail("null handle");
+  if (hi < lo) return fail("empty value range");
+  CU(cudaSetDevice(h->d.device));
+  const int64_t goff = (int64_t)h->g.g0 * h->plane;
+  randomize_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, goff, seed, lo, (uint32_t)(hi - lo + 1));
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int spk_cuda_pin_random(spk_cuda_handle *h, uint64_t seed, double fraction) {
+  if (!h) return fail("null handle");
+  if (h->d.model != SPK_POTTS_PIN) return fail("pin is only defined for app_style potts/pin");
+  if (fraction < 0.0 || fraction > 1.0) return fail("Illegal pin command");
+  CU(cudaSetDevice(h->d.device));
+  const int64_t goff = (int64_t)h->g.g0 * h->plane;
+  double t = std::floor(fraction * 4294967296.0);
+  const uint32_t thr = t > 4294967295.0 ? 4294967295u : (uint32_t)t;
+  pin_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, goff, seed, thr, h->d.nspins + 1);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int spk_cuda_sweep_color(spk_cuda_handle *h, uint32_t sweep, int color, const int32_t *box, int nloop) {
+  if (!h) return fail("null handle");
+  h->ev.sweep = sweep;
+  return sweep_set(h, RNG_PHILOX, color, box, nloop);
+}
+
+int spk_cuda_sweep_color_injected(spk_cuda_handle *h, int color, const int32_t *box, const double *u1,
+                                  const double *u2) {
+  if (!h || !u1 || !u2) return fail("null argument");
+  CU(cudaSetDevice(h->d.device));
+  const size_t bytes = (size_t)h->nlocal * sizeof(double);
+  if (!h->u1) {
+    CU(cudaMalloc(&h->u1, bytes));
+    CU(cudaMalloc(&h->u2, bytes));
+  }
+  CU(cudaMemcpyAsync(h->u1, u1, bytes, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->u2, u2, bytes, cudaMemcpyHostToDevice, h->stream));
+  int rc = sweep_set(h, RNG_INJECTED, color, box, 1);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));  // u1/u2 host buffers may be reused by the caller
+  return 0;
+}
+
+int spk_cuda_set_siteseeds(spk_cuda_handle *h, const int32_t *seeds, int64_t n) {
+  if (!h || !seeds) return fail("null argument");
+  if (n != h->nlocal) return fail("siteseeds size mismatch");
+  CU(cudaSetDevice(h->d.device));
+  if (!h->seeds) CU(cudaMalloc(&h->seeds, (size_t)n * sizeof(int32_t)));
+  CU(cudaMemcpyAsync(h->seeds, seeds, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int spk_cuda_get_siteseeds(spk_cuda_handle *h, int32_t *seeds, int64_t n) {
+  if (!h || !seeds) return fail("null argument");
+  if (!h->seeds) return fail("no siteseeds set");
+  if (n != h->nlocal) return fail("siteseeds size mismatch");
+  CU(cudaSetDevice(h->d.device));
+  CU(cudaMemcpyAsync(seeds, h->seeds, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int spk_cuda_sweep_color_strict(spk_cuda_handle *h, int color, const int32_t *box, int nloop) {
+  if (!h) return fail("null handle");
+  if (!h->seeds) return fail("sweep color/strict needs spk_cuda_set_siteseeds first");
+  return sweep_set(h, RNG_STRICT, color, box, nloop);
+}
+
+int spk_cuda_halo_exchange(spk_cuda_handle *h) {
+  if (!h) return fail("null handle");
+  if (h->d.nranks == 1) return 0;  // periodic images are read in place (Geo::lo_wrap / hi_wrap)
+  if (!h->comm) return fail("spk_cuda_comm_init has not been called");
+  CU(cudaSetDevice(h->d.device));
+  const int lower = (h->d.rank + h->d.nranks - 1) % h->d.nranks, upper = (h->d.rank + 1) % h->d.nranks;
+  const size_t n = (size_t)h->plane;
+  int32_t *first = h->spin, *last = h->spin + (int64_t)(h->nslab - 1) * h->plane;
+  int32_t *ghost_lo = h->base, *ghost_hi = h->spin + h->nlocal;
+  // the exchange runs on the compute stream's timeline: it must see the previous colour's
+  // writes and the next colour kernel must see the ghosts
+  NC(g_nccl.GroupStart());
+  NC(g_nccl.Send(first, n, ncclInt32, lower, h->comm, h->stream));
+  NC(g_nccl.Send(last, n, ncclInt32, upper, h->comm, h->stream));
+  NC(g_nccl.Recv(ghost_hi, n, ncclInt32, upper, h->comm, h->stream));
+  NC(g_nccl.Recv(ghost_lo, n, ncclInt32, lower, h->comm, h->stream));
+  NC(g_nccl.GroupEnd());
+  h->launches++;
+  return 0;
+}
+
+int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
+  if (!h) return fail("null handle");
+  if (nsweeps < 0) return fail("nsweeps must be >= 0");
+  for (int s = 0; s < nsweeps; s++) {
+    h->ev.sweep = first_sweep + (uint32_t)s;
+    for (int color = 1; color <= h->nc; color++) {
+      int rc = spk_cuda_halo_exchange(h);
+      if (rc) return rc;
+      rc = sweep_set(h, RNG_PHILOX, color, nullptr, 1);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+int spk_cuda_counters(spk_cuda_handle *h, int64_t *naccept, int64_t *nattempt) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->d.device));
+  unsigned long long acc = 0;
+  CU(cudaMemcpyAsync(&acc, h->naccept, sizeof acc, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (naccept) *naccept = (int64_t)acc;
+  if (nattempt) *nattempt = h->nattempt;
+  return 0;
+}
+
+int spk_cuda_reset_counters(spk_cuda_handle *h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->d.device));
+  CU(cudaMemsetAsync(h->naccept, 0, sizeof(unsigned long long), h->stream));
+  h->nattempt = 0;
+  return 0;
+}
+
+int spk_cuda_energy(spk_cuda_handle *h, double *energy) {
+  if (!h || !energy) return fail("null argument");
+  CU(cudaSetDevice(h->d.device));
+  int rc = spk_cuda_halo_exchange(h);  // DiagEnergy::compute calls comm->all() first (src/diag_energy.cpp:56)
+  if (rc) return rc;
+  CU(cudaMemsetAsync(h->escratch, 0, sizeof(unsigned long long), h->stream));
+  rc = launch_energy(h->d.lattice, h->stream, h->spin, h->g, h->escratch, &h->launches);
+  if (rc) return fail("energy kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  unsigned long long e = 0;
+  CU(cudaMemcpyAsync(&e, h->escratch, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *energy = (double)e;
+  return 0;
+}
+
+int spk_cuda_comm_id(char id[SPK_CUDA_COMM_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) <= SPK_CUDA_COMM_ID_BYTES, "ncclUniqueId larger than the ABI buffer");
+  if (!id) return fail("null argument");
+  if (nccl_bind()) return 1;
+  ncclUniqueId u;
+  NC(g_nccl.GetUniqueId(&u));
+  memset(id, 0, SPK_CUDA_COMM_ID_BYTES);
+  memcpy(id, &u, sizeof u);
+  return 0;
+}
+
+int spk_cuda_comm_init(spk_cuda_handle *h, const char id[SPK_CUDA_COMM_ID_BYTES]) {
+  if (!h || !id) return fail("null argument");
+  if (h->d.nranks == 1) return 0;
+  if (h->comm) return fail("communicator already initialised");
+  CU(cudaSetDevice(h->d.device));
+  if (nccl_bind()) return 1;
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof u);
+  NC(g_nccl.CommInitRank(&h->comm, h->d.nranks, u, h->d.rank));
+  return 0;
+}
+
+int spk_cuda_sync(spk_cuda_handle *h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->d.device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaStreamSynchronize(h->comm_stream));
+  return 0;
+}
+
+int spk_cuda_timer_start(spk_cuda_handle *h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->d.device));
+  CU(cudaEventRecord(h->t0, h->stream));
+  return 0;
+}
+
+int spk_cuda_timer_stop(spk_cuda_handle *h, float *ms) {
+  if (!h || !ms) return fail("null argument");
+  CU(cudaSetDevice(h->d.device));
+  CU(cudaEventRecord(h->t1, h->stream));
+  CU(cudaEventSynchronize(h->t1));
+  CU(cudaEventElapsedTime(ms, h->t0, h->t1));
+  return 0;
+}
+
+int spk_cuda_launch_count(spk_cuda_handle *h, int64_t *launches) {
+  if (!h || !launches) return fail("null argument");
+  *launches = h->launches;
+  return 0;
+}
+
+int spk_cuda_device_spins(spk_cuda_handle *h, void **dptr) {
+  if (!h || !dptr) return fail("null argument");
+  *dptr = h->spin;
+  return 0;
+}
+
+}  // extern "C"

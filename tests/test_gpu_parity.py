@@ -1,0 +1,183 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference fixtures and the oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from test_oracle_golden import GOLDEN, split_name
+
+pytestmark = pytest.mark.gpu
+
+
+def _sweep(model, lat, n, q, T, **kw):
+    from spparks_b200 import LatticeSweep
+    return LatticeSweep(model, lat, int(n[0]), int(n[1]), int(n[2]), nspins=int(q), temperature=float(T), **kw)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "half_*.npz"))), ids=os.path.basename)
+def test_injected_halfsweeps_bit_exact_vs_reference(path):
+    """Single colour half-sweeps with the reference's uniforms injected: integer spins bit-exact
+    against the UNMODIFIED reference (fixtures from oracle/_ref/ref_driver)."""
+    g = np.load(path)
+    model, lat = split_name(path, "half")
+    s = _sweep(model, lat, g["n"], g["q"], g["T"])
+    s.upload(g["spins0"])
+    prev = g["spins0"]
+    nacc = 0
+    for c in range(s.ncolors):
+        u1, u2 = O.injected_uniforms(g["k"][c])
+        s.sweep_color_injected(c + 1, u1, u2)
+        got = s.download()
+        assert np.array_equal(got, g["after"][c]), "colour %d" % (c + 1)
+        nacc += int(np.count_nonzero(got != prev))
+        prev = got
+    assert s.counters()[0] == nacc
+    assert s.energy() == float(g["energy"])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "sets_*.npz"))), ids=os.path.basename)
+def test_sector_color_sets_bit_exact_vs_reference(path):
+    g = np.load(path)
+    model, lat = split_name(path, "sets")
+    nx, ny, nz = [int(v) for v in g["n"]]
+    s = _sweep(model, lat, g["n"], g["q"], g["T"])
+    o = O.Oracle(model, lat, nx, ny, nz, int(g["q"]), float(g["T"]))
+    nsector = 4 if nz == 1 else 8
+    s.upload(g["spins0"])
+    u1, u2 = O.injected_uniforms(g["k"])
+    for sec in range(nsector):
+        box = o.sector_box(nsector, sec + 1)
+        for c in range(s.ncolors):
+            s.sweep_color_injected(c + 1, u1, u2, box=box)
+    assert np.array_equal(s.download(), g["after"])
+    assert s.counters()[1] == s.nlocal
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "strict_*.npz"))), ids=os.path.basename)
+def test_strict_runs_bit_exact_vs_reference(path):
+    """`sweep color/strict`: whole multi-sweep runs of the reference, spin for spin."""
+    g = np.load(path)
+    model, lat = split_name(path, "strict")
+    s = _sweep(model, lat, g["n"], g["q"], g["T"])
+    s.upload(g["spins0"])
+    s.set_siteseeds(g["seeds0"])
+    for _ in range(int(g["nsweeps"])):
+        for c in range(s.ncolors):
+            s.sweep_color_strict(c + 1)
+    assert np.array_equal(s.download(), g["after"])
+    assert np.array_equal(s.get_siteseeds(), g["seeds1"])
+    assert s.counters() == (int(g["naccept"]), int(g["nattempt"]))
+    assert s.energy() == float(g["energy"])
+
+
+CASES = [
+    ("ising", "sq/4n", (64, 48, 1), 2, 1.1346),
+    ("ising", "sq/4n", (50, 50, 1), 2, 0.0),
+    ("ising", "sc/6n", (16, 12, 10), 2, 2.25),
+    ("potts", "sq/8n", (34, 22, 1), 7, 0.6),
+    ("potts", "tri", (30, 17, 1), 9, 0.5),
+    ("potts", "sc/6n", (12, 10, 14), 4, 0.7),
+    ("potts", "sc/26n", (20, 14, 12), 100, 0.0),
+    ("potts", "sc/26n", (18, 12, 16), 6, 1.0),
+    ("potts/neighonly", "sc/26n", (20, 12, 14), 10000, 0.5),
+    ("potts/neighonly", "sc/26n", (16, 12, 10), 3, 0.0),
+    ("potts/neighonly", "tri", (20, 16, 1), 5, 0.4),
+    ("potts/neighonly", "sq/4n", (24, 24, 1), 3, 0.9),
+    ("potts/pin", "sc/26n", (16, 16, 12), 50, 0.5),
+    ("potts/pin", "sq/8n", (20, 20, 1), 8, 0.8),
+]
+
+
+@pytest.mark.parametrize("model,lat,n,q,T", CASES, ids=lambda v: str(v).replace(" ", ""))
+@pytest.mark.parametrize("force_generic", [False, True], ids=["tuned", "generic"])
+def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, force_generic, monkeypatch):
+    """Production (Philox) mode, three full sweeps, both the tuned and the generic kernels:
+    bit-exact against the oracle evaluating the same counter-based stream."""
+    if force_generic:
+        monkeypatch.setenv("SPK_CUDA_FORCE_GENERIC", "1")
+    rng = np.random.default_rng(7)
+    o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
+    spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=o.nsites, dtype=np.int32)
+    if model == "potts/pin":
+        spins[rng.random(o.nsites) < 0.05] = q + 1
+    s = _sweep(model, lat, n, q, T, seed=0xC0FFEE12345)
+    s.upload(spins)
+    want = spins.copy()
+    nacc = 0
+    for sw in range(3):
+        nacc += o.sweep_philox(want, 0xC0FFEE12345, 10 + sw)
+    s.sweeps(10, 3)
+    assert np.array_equal(s.download(), want)
+    assert s.counters() == (nacc, 3 * o.nsites)
+    assert s.energy() == o.total_energy(want)
+
+
+def test_per_colour_calls_equal_fused_sweeps():
+    """spk_cuda_sweeps == halo_exchange + sweep_color per colour (the contract of the fast path)."""
+    rng = np.random.default_rng(11)
+    n, q = (32, 24, 20), 12
+    spins = rng.integers(1, q + 1, size=n[0] * n[1] * n[2], dtype=np.int32)
+    a = _sweep("potts", "sc/26n", n, q, 0.7, seed=99)
+    b = _sweep("potts", "sc/26n", n, q, 0.7, seed=99)
+    a.upload(spins); b.upload(spins)
+    a.sweeps(0, 4)
+    for sw in range(4):
+        for c in range(1, 9):
+            b.halo_exchange()
+            b.sweep_color(sw, c)
+    assert np.array_equal(a.download(), b.download())
+    assert a.counters() == b.counters()
+
+
+def test_nloop_and_box_vs_oracle():
+    """nloop > 1 passes over one sector's colour set (src/app_lattice.cpp:674-676)."""
+    rng = np.random.default_rng(5)
+    n, q = (12, 10, 8), 5
+    o = O.Oracle("potts", "sc/26n", n[0], n[1], n[2], q, 0.9)
+    spins = rng.integers(1, q + 1, size=o.nsites, dtype=np.int32)
+    s = _sweep("potts", "sc/26n", n, q, 0.9, seed=4242)
+    s.upload(spins)
+    want = spins.copy()
+    box = o.sector_box(8, 6)
+    for c in range(1, 9):
+        for l in range(3):
+            o.halfsweep_philox(want, 4242, 7, c, iloop=l, box=box)
+        s.sweep_color(7, c, box=box, nloop=3)
+    assert np.array_equal(s.download(), want)
+
+
+def test_edge_sizes_and_errors():
+    from spparks_b200 import LatticeSweep, SpkCudaError
+    # smallest legal lattices: every neighbour is a periodic image
+    for model, lat, n, q in [("potts", "sc/26n", (2, 2, 2), 3), ("ising", "sq/4n", (2, 2, 1), 2),
+                             ("potts", "tri", (2, 1, 1), 4), ("potts/neighonly", "sq/8n", (2, 2, 1), 3)]:
+        o = O.Oracle(model, lat, n[0], n[1], n[2], q, 0.8)
+        rng = np.random.default_rng(3)
+        spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=o.nsites, dtype=np.int32)
+        s = _sweep(model, lat, n, q, 0.8, seed=5)
+        s.upload(spins)
+        want = spins.copy()
+        for sw in range(4):
+            o.sweep_philox(want, 5, sw)
+        s.sweeps(0, 4)
+        assert np.array_equal(s.download(), want), (model, lat)
+    with pytest.raises(SpkCudaError, match="incommensurate"):
+        LatticeSweep("potts", "sc/26n", 7, 8, 8, nspins=5)
+    with pytest.raises(SpkCudaError, match="nspins"):
+        LatticeSweep("potts", "sc/26n", 8, 8, 8, nspins=0)
+    s = LatticeSweep("potts", "sc/26n", 8, 8, 8, nspins=5)
+    with pytest.raises(SpkCudaError, match="colour"):
+        s.sweep_color(0, 9)
+    with pytest.raises(SpkCudaError, match="slab owns"):
+        s.upload(np.zeros(10, dtype=np.int32))
+
+
+def test_device_randomize_distribution():
+    s = _sweep("potts", "sc/26n", (64, 64, 64), 100, 0.0, seed=1)
+    s.randomize(12345, 1, 100)
+    a = s.download()
+    assert a.min() == 1 and a.max() == 100
+    counts = np.bincount(a, minlength=101)[1:]
+    assert abs(counts - a.size / 100).max() < 6 * np.sqrt(a.size / 100)
