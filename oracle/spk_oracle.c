@@ -338,14 +338,16 @@ int64_t orc_halfsweep_injected(const orc_ctx *c, int32_t *spin, int color, const
   return acc;
 }
 
-/* Philox production mode.  Counter = (site lo, site hi, sweep, iloop*16+color), key = seed;
- * word 0 plays u1 = w0/2^32 and word 1 plays u2 = w1/2^32.  With those exactly representable
- * uniforms the reference's double formulas reduce to the integer forms below, which is what
- * the CUDA kernels evaluate:
- *   ising:      u1 < 0.5            <=>  w0 < 2^31
- *   potts/pin:  (int)(Q*u1)+1        =   ((Q*w0) >> 32) + 1          (Q < 2^31)
- *   neighonly:  (int)(nevent*u1)     =   (nevent*w0) >> 32
- *   reject:     u2 > p               <=>  w1 > floor(p*2^32),  p = exp(-dE/T) from libm on the host */
+/* Philox production mode.  One Philox4x32-10 block serves the PAIR of same-colour sites whose
+ * cell index i differs only in bit 1 (i and i^2, same j,k,basis): counter = (leader lo, leader hi,
+ * sweep, iloop*16+color) with leader = index of the site with bit 1 of i cleared, key = seed.
+ * The site with bit 1 clear consumes words (0,1), the other one words (2,3); the first word plays
+ * u1 = w/2^32 and the second u2.  With those exactly representable uniforms the reference's
+ * double formulas reduce to the integer forms below, which is what the CUDA kernels evaluate:
+ *   ising:      u1 < 0.5            <=>  w < 2^31
+ *   potts/pin:  (int)(Q*u1)+1        =   ((Q*w) >> 32) + 1          (Q < 2^31)
+ *   neighonly:  (int)(nevent*u1)     =   (nevent*w) >> 32
+ *   reject:     u2 > p               <=>  w' > floor(p*2^32),  p = exp(-dE/T) from libm on the host */
 uint32_t orc_accept_threshold(double temperature, int dE) {
   double p = exp((0.0 - (double)dE) * (1.0 / temperature));
   double t = floor(p * 4294967296.0);
@@ -358,10 +360,14 @@ static int philox_event(const orc_ctx *c, int32_t *spin, int64_t site, uint64_t 
   const int Q = c->cfg.nspins, nn = c->maxneigh;
   int old = spin[site];
   if (c->cfg.model == ORC_POTTS_PIN && old > Q) return 0;
-  uint32_t ctr[4] = {(uint32_t)site, (uint32_t)((uint64_t)site >> 32), sweep,
-                     (uint32_t)iloop * 16u + (uint32_t)color};
-  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, w[4];
-  orc_philox4x32_10(ctr, key, w);
+  int ci, cj, ck, cm;
+  site_ijkm(c, site, &ci, &cj, &ck, &cm);
+  const int second = (ci >> 1) & 1;
+  const uint64_t leader = (uint64_t)site - (second ? 2u * (uint64_t)c->nbasis : 0u);
+  uint32_t ctr[4] = {(uint32_t)leader, (uint32_t)(leader >> 32), sweep, (uint32_t)iloop * 16u + (uint32_t)color};
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, blk[4], w[2];
+  orc_philox4x32_10(ctr, key, blk);
+  w[0] = blk[2 * second]; w[1] = blk[2 * second + 1];
 
   int64_t nb[ORC_MAXNEIGH];
   orc_neighbors(c, site, nb);

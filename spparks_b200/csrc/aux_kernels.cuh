@@ -10,7 +10,7 @@ __global__ void randomize_kernel(int32_t *spin, long long n, long long goff, uns
                                  uint32_t range) {
   for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n; s += (long long)gridDim.x * blockDim.x) {
     unsigned long long gs = (unsigned long long)(s + goff);
-    uint2 w = philox4x32_10_w01((uint32_t)gs, (uint32_t)(gs >> 32), 0x5e7517e5u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint4 w = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), 0x5e7517e5u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
     spin[s] = lo + (int)__umulhi(range, w.x);
   }
 }
@@ -22,7 +22,7 @@ __global__ void pin_kernel(int32_t *spin, long long n, long long goff, unsigned 
                            int pinned) {
   for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n; s += (long long)gridDim.x * blockDim.x) {
     unsigned long long gs = (unsigned long long)(s + goff);
-    uint2 w = philox4x32_10_w01((uint32_t)gs, (uint32_t)(gs >> 32), 0x9199ed51u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint4 w = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), 0x9199ed51u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32));
     if (w.x < thr) spin[s] = pinned;
   }
 }

@@ -1,6 +1,7 @@
 // Per-site rejection event (site_event_rejection of the four apps) and the random sources.
 #pragma once
 #include <stdint.h>
+#include "dedupe_chain.cuh"
 #include "lattice.cuh"
 
 namespace spk {
@@ -8,15 +9,16 @@ namespace spk {
 enum { RNG_PHILOX = 0, RNG_INJECTED = 1, RNG_STRICT = 2 };
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al. SC'11).  counter = (site lo, site hi, sweep, iloop*16 + colour),
-// key = seed.  Only words 0 and 1 of the output block are consumed (u1, u2).
-// The key schedule is warp-uniform, so it folds into immediates/uniform registers.
-__device__ __forceinline__ uint2 philox4x32_10_w01(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                   uint32_t k0, uint32_t k1) {
+// Philox4x32-10 (Salmon et al. SC'11).  One block serves the PAIR of same-colour sites whose cell
+// index i differs only in bit 1: counter = (leader lo, leader hi, sweep, iloop*16 + colour) with
+// leader = global index of the site with bit 1 of i cleared; key = seed.  The site with bit 1
+// clear takes words (x,y), the other one (z,w).  The key schedule is warp-uniform.
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ k0;
     c2 = hi0 ^ c3 ^ k1;
     c1 = lo1;
@@ -24,13 +26,13 @@ __device__ __forceinline__ uint2 philox4x32_10_w01(uint32_t c0, uint32_t c1, uin
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
-  return make_uint2(c0, c1);
+  return make_uint4(c0, c1, c2, c3);
 }
 
 // RandomPark::uniform (src/random_park.cpp:79-86) as 16807*seed mod (2^31-1); the Schrage form
 // of the reference and this 64-bit product give the same residue for seed in [1, 2^31-2].
 __device__ __forceinline__ double park_uniform(int &seed) {
-  uint64_t p = (uint64_t)16807u * (uint32_t)seed;
+  const uint64_t p = (uint64_t)16807u * (uint32_t)seed;
   uint32_t s = (uint32_t)(p & 0x7FFFFFFFu) + (uint32_t)(p >> 31);
   if (s >= 0x7FFFFFFFu) s -= 0x7FFFFFFFu;
   seed = (int)s;
@@ -41,34 +43,56 @@ __device__ __forceinline__ double park_uniform(int &seed) {
 struct EventParams {
   int nspins;               // Q
   int t_zero;               // temperature == 0.0
+  int one;                  // the constant 1, opaque to the compiler (see unlike())
   uint32_t k0, k1;          // Philox key (seed)
   uint32_t sweep;           // Philox counter word 2
   uint32_t thr[27];         // Philox mode: floor(exp(-dE/T) * 2^32), dE = 1..26 (host libm)
   double ptab[27];          // double modes: exp((double)(-dE) * t_inverse)       (host libm)
 };
 
-// Source of the (at most) two uniforms of one event; drawn lazily like random->uniform().
+// Source of the (at most) two uniforms of one event; the double modes draw lazily like
+// random->uniform() does.
 template <int RNG> struct Draws;
+template <> struct Draws<RNG_PHILOX> { uint32_t w1, w2; };
+template <> struct Draws<RNG_INJECTED> { double u1, u2; };
+template <> struct Draws<RNG_STRICT> { int seed; };
 
-template <> struct Draws<RNG_PHILOX> {
-  uint2 w;
-  __device__ __forceinline__ Draws(const EventParams &p, uint64_t gsite, uint32_t c3) {
-    w = philox4x32_10_w01((uint32_t)gsite, (uint32_t)(gsite >> 32), p.sweep, c3, p.k0, p.k1);
-  }
-};
-template <> struct Draws<RNG_INJECTED> {
-  double u1, u2;
-};
-template <> struct Draws<RNG_STRICT> {
-  int seed;
-};
-
-// number of neighbours unlike `value`  (site_energy, src/app_potts.cpp:97-104)
-template <int NN> __device__ __forceinline__ int unlike(const int (&v)[NN], int value) {
-  int e = 0;
+// number of neighbours unlike `value`  (site_energy, src/app_potts.cpp:97-104).
+// Each compare is one ISETP (ALU pipe) plus one predicated IMAD (FMA pipe): `one` is the value 1
+// passed through kernel parameters so that ptxas keeps the multiply-add form and the two integer
+// pipes stay balanced; nvcc's own code for `e += (v != s)` costs 2.4-3.2 ALU-heavy instructions.
+template <int NN> __device__ __forceinline__ int unlike(const int (&v)[NN], int value, int one) {
+  int e[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int n = 0; n < NN; n++) e += (v[n] != value);
-  return e;
+  for (int n = 0; n < NN; n++)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, %2;\n\t@p mad.lo.s32 %0, %3, %3, %0;\n\t}"
+        : "+r"(e[n & 3]) : "r"(v[n]), "r"(value), "r"(one));
+  return (e[0] + e[1]) + (e[2] + e[3]);
+}
+
+// position of the pick-th (0-based) set bit of m; pick < popc(m)
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int pick) {
+  int pos = 0;
+#pragma unroll
+  for (int width = 16; width >= 1; width >>= 1) {
+    const int c = __popc(m & ((1u << width) - 1u));
+    if (pick >= c) { pick -= c; m >>= width; pos += width; }
+  }
+  return pos;
+}
+
+// v[pos] for a register-resident array: binary select tree on the bits of pos
+template <int NN> __device__ __forceinline__ int select_slot(const int (&v)[NN], int pos) {
+  int t[32];
+#pragma unroll
+  for (int n = 0; n < 32; n++) t[n] = v[n < NN ? n : NN - 1];
+#pragma unroll
+  for (int bit = 0, len = 32; bit < 5; bit++, len >>= 1) {
+    const bool hi = (pos >> bit) & 1;
+#pragma unroll
+    for (int n = 0; n < len / 2; n++) t[n] = hi ? t[2 * n + 1] : t[2 * n];
+  }
+  return t[0];
 }
 
 // One site_event_rejection.  `old` = spin[i], v[] = neighbour spins in reference order.
@@ -78,24 +102,18 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
   const int Q = p.nspins;
   if (MODEL == SPK_POTTS_PIN && old > Q) return old;  // pinned: no draw (src/app_potts_pin.cpp:97)
 
-  const int e0 = unlike<NN>(v, old);
+  const int e0 = unlike<NN>(v, old, p.one);
   int trial;
 
   if constexpr (MODEL == SPK_POTTS_NEIGHONLY) {
-    // distinct neighbour values != old in first-occurrence order (src/app_potts_neighonly.cpp:81-88)
-    uint32_t first = 0;
-#pragma unroll
-    for (int n = 0; n < NN; n++) {
-      bool dup = (v[n] == old);
-#pragma unroll
-      for (int q = 0; q < n; q++) dup = dup || (v[q] == v[n]);
-      first |= dup ? 0u : (1u << n);
-    }
+    // candidates = distinct neighbour values != old, first-occurrence order
+    // (src/app_potts_neighonly.cpp:81-88); bit n of `first` marks slot n as a new candidate
+    if (e0 == 0) return old;  // nevent == 0: no draw (src/app_potts_neighonly.cpp:90)
+    const uint32_t first = first_occurrence_mask<NN>(v, old);
     const int nevent = __popc(first);
-    if (nevent == 0) return old;  // no draw (src/app_potts_neighonly.cpp:90)
     int pick;
     if constexpr (RNG == RNG_PHILOX) {
-      pick = (int)__umulhi((uint32_t)nevent, d.w.x);
+      pick = (int)__umulhi((uint32_t)nevent, d.w1);
     } else {
       double u;
       if constexpr (RNG == RNG_INJECTED) u = d.u1;
@@ -103,19 +121,10 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
       pick = (int)(nevent * u);
       if (pick >= nevent) pick = nevent - 1;
     }
-    // value of the pick-th set bit of `first`
-    trial = old;
-    int seen = 0;
-#pragma unroll
-    for (int n = 0; n < NN; n++) {
-      bool f = (first >> n) & 1u;
-      if (f && seen == pick) trial = v[n];
-      seen += f;
-    }
+    trial = select_slot<NN>(v, nth_set_bit(first, pick));
   } else if constexpr (RNG == RNG_PHILOX) {
-    const uint32_t w0 = d.w.x;
-    if (MODEL == SPK_ISING) trial = (w0 < 0x80000000u) ? 1 : 2;
-    else trial = (int)__umulhi((uint32_t)Q, w0) + 1;
+    if (MODEL == SPK_ISING) trial = (d.w1 < 0x80000000u) ? 1 : 2;
+    else trial = (int)__umulhi((uint32_t)Q, d.w1) + 1;
   } else {
     double u;
     if constexpr (RNG == RNG_INJECTED) u = d.u1;
@@ -127,13 +136,13 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
     }
   }
 
-  const int e1 = unlike<NN>(v, trial);
+  const int e1 = unlike<NN>(v, trial, p.one);
   if (e1 <= e0) return trial;
   if (p.t_zero) return old;
   const int dE = e1 - e0;
   bool reject;
   if constexpr (RNG == RNG_PHILOX) {
-    reject = d.w.y > p.thr[dE];
+    reject = d.w2 > p.thr[dE];
   } else {
     double u;
     if constexpr (RNG == RNG_INJECTED) u = d.u2;

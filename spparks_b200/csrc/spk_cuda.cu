@@ -103,6 +103,7 @@ void build_tables(spk_cuda_handle *h) {
   EventParams &ev = h->ev;
   ev.nspins = h->d.model == SPK_ISING ? 2 : h->d.nspins;
   ev.t_zero = h->d.temperature == 0.0;
+  ev.one = 1;
   ev.k0 = (uint32_t)h->d.seed;
   ev.k1 = (uint32_t)(h->d.seed >> 32);
   ev.sweep = 0;
@@ -266,7 +267,8 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
   if (desc->temperature < 0.0) return fail("temperature must be >= 0");
   if (desc->nranks < 1 || desc->rank < 0 || desc->rank >= desc->nranks) return fail("bad rank/nranks");
   const int nslab_g = dim == 3 ? nz : desc->ny;
-  if (nslab_g % desc->nranks || (nslab_g / desc->nranks) % 2 || nslab_g / desc->nranks < 2)
+  // slabs must keep the colour parity of the global lattice (even thickness) and hold >= 2 layers
+  if (desc->nranks > 1 && (nslab_g % desc->nranks || (nslab_g / desc->nranks) % 2 || nslab_g / desc->nranks < 2))
     return fail("slab dimension %d does not split into %d even slabs", nslab_g, desc->nranks);
 
   int ndev = 0;

@@ -87,6 +87,21 @@ CASES = [
     ("potts/neighonly", "sq/4n", (24, 24, 1), 3, 0.9),
     ("potts/pin", "sc/26n", (16, 16, 12), 50, 0.5),
     ("potts/pin", "sq/8n", (20, 20, 1), 8, 0.8),
+    # row lengths that are multiples of 8 elements: the tuned strip kernel takes these
+    ("ising", "sq/4n", (256, 34, 1), 2, 1.1346),
+    ("ising", "sq/8n", (40, 22, 1), 2, 2.0),
+    ("potts", "sq/8n", (72, 18, 1), 7, 0.6),
+    ("potts", "tri", (36, 11, 1), 9, 0.5),
+    ("potts", "tri", (128, 6, 1), 3, 0.0),
+    ("potts", "sc/6n", (24, 10, 14), 4, 0.7),
+    ("potts", "sc/26n", (24, 14, 12), 100, 0.0),
+    ("potts", "sc/26n", (264, 6, 4), 6, 1.0),
+    ("potts", "sc/26n", (8, 8, 8), 3, 0.4),
+    ("potts/neighonly", "sc/26n", (32, 12, 14), 10000, 0.5),
+    ("potts/neighonly", "sc/26n", (16, 12, 10), 3, 0.0),
+    ("potts/neighonly", "tri", (20, 16, 1), 5, 0.4),
+    ("potts/neighonly", "sq/4n", (24, 24, 1), 3, 0.9),
+    ("potts/pin", "sc/26n", (48, 10, 6), 50, 0.5),
 ]
 
 
@@ -131,10 +146,11 @@ def test_per_colour_calls_equal_fused_sweeps():
     assert a.counters() == b.counters()
 
 
-def test_nloop_and_box_vs_oracle():
+@pytest.mark.parametrize("n", [(12, 10, 8), (32, 10, 8)], ids=["generic", "strip"])
+def test_nloop_and_box_vs_oracle(n):
     """nloop > 1 passes over one sector's colour set (src/app_lattice.cpp:674-676)."""
     rng = np.random.default_rng(5)
-    n, q = (12, 10, 8), 5
+    q = 5
     o = O.Oracle("potts", "sc/26n", n[0], n[1], n[2], q, 0.9)
     spins = rng.integers(1, q + 1, size=o.nsites, dtype=np.int32)
     s = _sweep("potts", "sc/26n", n, q, 0.9, seed=4242)
@@ -152,7 +168,7 @@ def test_edge_sizes_and_errors():
     from spparks_b200 import LatticeSweep, SpkCudaError
     # smallest legal lattices: every neighbour is a periodic image
     for model, lat, n, q in [("potts", "sc/26n", (2, 2, 2), 3), ("ising", "sq/4n", (2, 2, 1), 2),
-                             ("potts", "tri", (2, 1, 1), 4), ("potts/neighonly", "sq/8n", (2, 2, 1), 3)]:
+                             ("potts", "tri", (2, 2, 1), 4), ("potts/neighonly", "sq/8n", (2, 2, 1), 3)]:
         o = O.Oracle(model, lat, n[0], n[1], n[2], q, 0.8)
         rng = np.random.default_rng(3)
         spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=o.nsites, dtype=np.int32)
