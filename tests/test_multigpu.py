@@ -1,0 +1,19 @@
+"""N-GPU == 1-GPU bit-exactness, launched as one process per GPU under torchrun."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_two_slabs_equal_one_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "MGPU_ALL_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
