@@ -1,0 +1,253 @@
+/* ----------------------------------------------------------------------
+   SPPARKS app-style plugin: `/cuda` variants of ising, potts, potts/neighonly, potts/pin.
+
+   Drop these files into the SPPARKS src/ directory (or add them to the build as
+   plugin/Makefile does), rebuild, and `app_style potts/cuda 100` runs the rejection-KMC
+   colour sweep of an unchanged input script on a B200 through libspparks_cuda
+   (include/spparks_cuda.h).  Registration goes through style_app.h exactly like the
+   reference's own apps (src/app_potts_neighonly.h:18-42, src/Make.sh:8-45).
+
+   AppCudaMixin<Base,MODEL> derives from the reference app (AppIsing, AppPotts, ...) so that
+   site_energy(), stats(), dumps, diagnostics and the `pin` command keep working on the host
+   copy of the spins; it overrides
+     init_app()           validate geometry, create the device lattice   (src/app_lattice.cpp:318)
+     iterate_rejection()  the sweep loop, one kernel launch per set      (src/app_lattice.cpp:632-711)
+     input_app()          extra commands cuda_device / cuda_seed
+   Host spins (iarray[0]) are current whenever control leaves iterate_rejection() or
+   output->compute() runs, as SURVEY §8b requires.
+------------------------------------------------------------------------- */
+
+#ifndef SPK_APP_CUDA_MIXIN_H
+#define SPK_APP_CUDA_MIXIN_H
+
+#include "mpi.h"
+#include "string.h"
+#include "stdlib.h"
+#include "stdint.h"
+#include "app_lattice.h"
+#include "comm_lattice.h"
+#include "domain.h"
+#include "lattice.h"
+#include "random_mars.h"
+// output.h has no include guard in the reference: input.cpp includes it before style_app.h
+#include "timer.h"
+#include "error.h"
+
+#include "spparks_cuda.h"
+
+namespace SPPARKS_NS {
+
+template <class Base, int MODEL>
+class AppCudaMixin : public Base {
+ public:
+  AppCudaMixin(class SPPARKS *spk, int narg, char **arg) : Base(spk,narg,arg)
+  {
+    // Base parsed its arguments only if style matched its own name
+    // (src/app_potts.cpp:47, src/app_potts_neighonly.cpp:36), so do it here
+    if constexpr (MODEL == SPK_ISING) {
+      if (narg != 1) this->error->all(FLERR,"Illegal app_style command");
+      nspins_cuda = 2;
+    } else {
+      if (narg != 2) this->error->all(FLERR,"Illegal app_style command");
+      this->nspins = atoi(arg[1]);
+      if (this->nspins <= 0) this->error->all(FLERR,"Illegal app_style command");
+      this->dt_sweep = 1.0/this->nspins;
+      nspins_cuda = this->nspins;
+    }
+    this->allow_kmc = 0;          // the device path is rejection KMC only
+    this->allow_masking = 0;
+    handle = NULL;
+    device = 0;
+    seed_set = 0;
+    seed = 0;
+    sweep_counter = 0;
+    warned = 0;
+  }
+
+  virtual ~AppCudaMixin() { if (handle) spk_cuda_destroy(handle); }
+
+  void input_app(char *command, int narg, char **arg)
+  {
+    if (strcmp(command,"cuda_device") == 0) {
+      if (narg != 1) this->error->all(FLERR,"Illegal cuda_device command");
+      device = atoi(arg[0]);
+    } else if (strcmp(command,"cuda_seed") == 0) {
+      if (narg != 1) this->error->all(FLERR,"Illegal cuda_seed command");
+      seed = strtoull(arg[0],NULL,10);
+      seed_set = 1;
+    } else Base::input_app(command,narg,arg);
+  }
+
+  void init_app()
+  {
+    Base::init_app();   // spin validity check, dt_sweep of potts/neighonly
+
+    // the device kernels address sites by lattice index: need a `create_sites box` lattice
+    // that is fully periodic (domain->nx,ny,nz set, src/create_sites.cpp:248-252) and
+    // one of the five supported styles (enum of src/lattice.cpp:32-33)
+
+    Domain *domain = this->domain;
+    if (domain->lattice == NULL || domain->nx == 0)
+      this->error->all(FLERR,"app_style */cuda requires create_sites box on a periodic lattice");
+    int lat = domain->lattice->style;
+    if (spk_cuda_maxneigh(lat) == 0 || this->maxneigh != spk_cuda_maxneigh(lat))
+      this->error->all(FLERR,"app_style */cuda does not support this lattice style");
+
+    // one process <-> one GPU; with several ranks every rank must own one slab of the
+    // last dimension (processors 1 1 P in 3d, 1 P 1 in 2d)
+
+    int sd = domain->dimension - 1;
+    for (int d = 0; d < 3; d++)
+      if (d != sd && domain->procgrid[d] != 1)
+        this->error->all(FLERR,"app_style */cuda needs a slab decomposition (processors 1 1 P)");
+    if (this->nprocs > 1 && domain->myloc[sd] != this->me)
+      this->error->all(FLERR,"app_style */cuda needs slab index == MPI rank");
+
+    tagint first = this->nlocal ? this->id[0] : 1;
+    for (int i = 0; i < this->nlocal; i++)
+      if (this->id[i] != first+i)
+        this->error->all(FLERR,"app_style */cuda requires sites ordered by ID");
+
+    if (!seed_set) {
+      // like ranapp (src/app_lattice.cpp:274-278): derived from the `seed` command, once
+      seed = (uint64_t) (this->ranmaster->uniform() * 9007199254740992.0);
+      seed_set = 1;
+    }
+
+    if (handle) { spk_cuda_destroy(handle); handle = NULL; }
+
+    spk_cuda_desc desc;
+    desc.model = MODEL;
+    desc.lattice = lat;
+    desc.nx = domain->nx; desc.ny = domain->ny; desc.nz = domain->nz;
+    desc.nspins = nspins_cuda;
+    desc.temperature = this->temperature;
+    desc.seed = seed;
+    desc.device = device;
+    desc.rank = this->me;
+    desc.nranks = this->nprocs;
+    check(spk_cuda_create(&desc,&handle));
+    if (spk_cuda_nlocal(handle) != this->nlocal)
+      this->error->one(FLERR,"app_style */cuda: slab size does not match nlocal");
+
+    if (this->nprocs > 1) {
+      char id[SPK_CUDA_COMM_ID_BYTES];
+      if (this->me == 0) check(spk_cuda_comm_id(id));
+      MPI_Bcast(id,SPK_CUDA_COMM_ID_BYTES,MPI_CHAR,0,this->world);
+      check(spk_cuda_comm_init(handle,id));
+    }
+  }
+
+  // replaces AppLattice::iterate_rejection (src/app_lattice.cpp:632-711)
+
+  void iterate_rejection(double stoptime)
+  {
+    // same enum as src/app_lattice.cpp:40 (file-local there)
+    enum{NOSWEEP,RANDOM,RASTER,COLOR,COLOR_STRICT};
+
+    if (this->Lmask) this->error->all(FLERR,"Mask logic not implemented in app");
+    int lat = this->domain->lattice->style;
+    int ncolor = spk_cuda_ncolors(lat);
+    int strict = (this->sweepflag == COLOR_STRICT);
+
+    if ((this->sweepflag == RANDOM || this->sweepflag == RASTER) && !warned && this->me == 0) {
+      this->error->warning(FLERR,"app_style */cuda runs sweep random/raster as colour sweeps "
+                           "(same attempts per site and time step; statistically equivalent)");
+      warned = 1;
+    }
+
+    check(spk_cuda_set_temperature(handle,this->temperature));
+    check(spk_cuda_upload_spins(handle,this->iarray[0],this->nlocal));
+    if (strict) check(spk_cuda_set_siteseeds(handle,this->siteseeds,this->nlocal));
+    check(spk_cuda_reset_counters(handle));
+    bigint naccept0 = this->naccept;
+    bigint nattempt0 = this->nattempt;
+
+    // sets: sectors (or the whole domain) x colours; with RANDOM/RASTER the reference has
+    // one set per sector and nloop/nselect chosen so that every site is attempted nstop times
+
+    int nsector = this->nsector;
+    int done = 0;
+    while (!done) {
+      this->timer->stamp();
+      for (int isector = 0; isector < nsector; isector++) {
+        int box[6];
+        sector_box(isector,nsector,box);
+        for (int icolor = 0; icolor < ncolor; icolor++) {
+          int nloop = set_nloop(isector,icolor,ncolor);
+          if (nloop < 1) continue;
+          check(spk_cuda_halo_exchange(handle));      // comm->all(), src/app_lattice.cpp:650-651
+          if (strict)
+            check(spk_cuda_sweep_color_strict(handle,icolor+1,nsector > 1 ? box : NULL,nloop));
+          else
+            check(spk_cuda_sweep_color(handle,sweep_counter,icolor+1,nsector > 1 ? box : NULL,nloop));
+        }
+      }
+      sweep_counter++;
+      this->nsweeps++;
+      this->time += this->dt_rkmc;
+      if (this->time >= stoptime) done = 1;
+
+      if (done || this->time >= this->nextoutput) {
+        // host copy must be current before diagnostics, stats and dumps read it
+        check(spk_cuda_download_spins(handle,this->iarray[0],this->nlocal));
+        int64_t acc,att;
+        check(spk_cuda_counters(handle,&acc,&att));
+        this->naccept = naccept0 + acc;
+        this->nattempt = nattempt0 + att;
+        this->timer->stamp(TIME_SOLVE);
+        this->nextoutput = this->output->compute(this->time,done);
+        this->timer->stamp(TIME_OUTPUT);
+      }
+    }
+    if (strict) check(spk_cuda_get_siteseeds(handle,this->siteseeds,this->nlocal));
+  }
+
+ private:
+  spk_cuda_handle *handle;
+  int device,nspins_cuda,seed_set,warned;
+  uint64_t seed;
+  uint32_t sweep_counter;
+
+  void check(int rc)
+  {
+    if (rc) this->error->one(FLERR,spk_cuda_last_error());
+  }
+
+  // sector of create_set() (src/app_lattice.cpp:969-984) as a box of global cell indices:
+  // x < xmid  <=>  i < ceil(nx/2) for every basis site of the supported lattices
+
+  void sector_box(int isector, int nsector, int *box)
+  {
+    int nx = this->domain->nx, ny = this->domain->ny, nz = this->domain->nz;
+    box[0] = 0; box[1] = nx; box[2] = 0; box[3] = ny; box[4] = 0; box[5] = nz;
+    if (nsector == 1) return;
+    int hx = (nx+1)/2, hy = (ny+1)/2, hz = (nz+1)/2;
+    if (isector & 1) box[0] = hx; else box[1] = hx;
+    if (nsector >= 4) { if (isector & 2) box[2] = hy; else box[3] = hy; }
+    if (nsector == 8) { if (isector & 4) box[4] = hz; else box[5] = hz; }
+  }
+
+  // nloop of the reference's set for (sector,colour) (src/app_lattice.cpp:401-410)
+
+  int set_nloop(int isector, int icolor, int ncolor)
+  {
+    enum{NOSWEEP,RANDOM,RASTER,COLOR,COLOR_STRICT};
+    int iset;
+    if (this->sweepflag == COLOR || this->sweepflag == COLOR_STRICT) {
+      if (this->bothflag) iset = this->nsector + isector*ncolor + icolor;
+      else iset = icolor;
+      return this->set[iset].nloop;
+    }
+    // RANDOM / RASTER: one set per sector; nselect/nlocal attempts per site
+    iset = isector;
+    if (this->sweepflag == RASTER) return this->set[iset].nloop;
+    if (this->set[iset].nlocal == 0) return 0;
+    int n = this->set[iset].nselect / this->set[iset].nlocal;
+    return n < 1 ? 1 : n;
+  }
+};
+
+}
+
+#endif

@@ -1,0 +1,116 @@
+"""The drop-in: unchanged SPPARKS input scripts with `app_style <name>/cuda`, run by the reference
+host (unmodified objects) + plugin/ + libspparks_cuda  (plugin/_build/spk_cuda), next to the
+unmodified reference binary (oracle/_ref/spk_ref).  Both binaries are prebuilt in the build
+container and travel to the GPU box; the tests skip if they are absent."""
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SPK_CUDA = os.path.join(ROOT, "plugin", "_build", "spk_cuda")
+SPK_REF = os.path.join(ROOT, "oracle", "_ref", "spk_ref")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (os.path.exists(SPK_CUDA) and os.path.exists(SPK_REF)),
+                                 reason="plugin/_build/spk_cuda or oracle/_ref/spk_ref not built")]
+
+
+def run(binary, script):
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "in.script")
+        open(path, "w").write(script)
+        out = subprocess.run([binary, "-in", path, "-log", "none"], cwd=tmp, capture_output=True, text=True,
+                             timeout=600)
+    assert "ERROR" not in out.stdout, out.stdout[-2000:]
+    return out.stdout
+
+
+def stats_rows(text):
+    """rows of every stats table: (time, naccept, nreject, nsweeps, extra columns without CPU)"""
+    rows, on = [], False
+    for line in text.splitlines():
+        f = line.split()
+        if f[:2] == ["Time", "Naccept"]:
+            on = True
+            continue
+        if on:
+            if f and f[0] == "WARNING:":
+                continue
+            if len(f) >= 5 and re.match(r"^[0-9.eE+-]+$", f[0]):
+                rows.append(tuple(f[:4] + f[5:]))
+            else:
+                on = False
+    return rows
+
+
+STRICT = """seed 4711
+app_style {app}
+dimension {dim}
+lattice {lat} 1.0
+region box block 0 {nx} 0 {ny} {zr}
+create_box box
+create_sites box
+set site range 1 {hi}
+{extra}
+sweep color/strict
+sector no
+temperature {T}
+diag_style energy
+stats {stats}
+run {run}
+run {run}
+"""
+
+STRICT_CASES = [
+    dict(app="potts", q=20, dim=3, lat="sc/26n", nx=16, ny=12, zr="0 10", hi=20, T=0.8, stats=0.1, run=0.5, extra=""),
+    dict(app="potts/neighonly", q=30, dim=3, lat="sc/26n", nx=16, ny=8, zr="0 12", hi=30, T=0.5, stats=0.5, run=1.0,
+         extra=""),
+    dict(app="potts/pin", q=12, dim=3, lat="sc/26n", nx=8, ny=8, zr="0 8", hi=12, T=1.0, stats=0.25, run=0.5,
+         extra="pin 0.05 0 0"),
+    dict(app="ising", q=0, dim=2, lat="sq/4n", nx=64, ny=32, zr="-0.5 0.5", hi=2, T=1.1346, stats=2.0, run=10.0,
+         extra=""),
+    dict(app="potts", q=9, dim=2, lat="tri", nx=16, ny=10, zr="-0.5 0.5", hi=9, T=0.5, stats=0.5, run=1.0, extra=""),
+]
+
+
+@pytest.mark.parametrize("case", STRICT_CASES, ids=lambda c: c["app"] + "-" + c["lat"])
+def test_color_strict_script_identical_to_reference(case):
+    """`sweep color/strict` makes the reference independent of traversal order, so the GPU run of
+    the same script must print the same Naccept / Nreject / Nsweeps / Energy table, over two
+    consecutive `run` commands."""
+    def script(style):
+        app = style if case["app"] == "ising" else "%s %d" % (style, case["q"])
+        return STRICT.format(**dict(case, app=app))
+    ref = stats_rows(run(SPK_REF, script(case["app"])))
+    gpu = stats_rows(run(SPK_CUDA, script(case["app"] + "/cuda")))
+    assert len(ref) >= 4 and gpu == ref
+
+
+def test_in_ising_with_cuda_style():
+    """examples/ising/in.ising with only the style name changed (sweep random is mapped to colour
+    sweeps): same attempts, sweeps and time axis; energy relaxes as in the shipped log
+    (examples/ising/log.ising.11Nov09.linux.1: 5112 -> 320)."""
+    script = """seed 56789
+app_style ising/cuda
+dimension 2
+lattice sq/4n 1.0
+region box block 0 50 0 50 -0.5 0.5
+create_box box
+create_sites box
+set site range 1 2
+sweep random
+sector yes
+diag_style energy
+temperature 0.0
+stats 10.0
+run 100.0
+"""
+    rows = stats_rows(run(SPK_CUDA, script))
+    assert len(rows) == 11
+    assert rows[0][4] == "5112"  # same `set site range` stream as the reference
+    assert [r[3] for r in rows] == [str(20 * i) for i in range(11)]
+    assert int(rows[-1][1]) + int(rows[-1][2]) == 500000
+    assert 150 <= float(rows[-1][4]) <= 700

@@ -1,0 +1,89 @@
+"""Full-run statistical agreement (the RNG streams necessarily differ from the reference's):
+2-D Ising against Onsager's exact solution, Potts grain growth against the reference's curve."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def onsager(T):
+    """Exact 2-D Ising results in SPPARKS units: the Boltzmann factor is exp(-dN/T) with dN the
+    change in unlike neighbours of the flipped site, i.e. T = k_B T_phys / 2J and 2*beta*J = 1/T
+    (T_c = 1/ln(1+sqrt 2) = 1.134593).  Returns (|m|, <site_energy>) with site_energy = number of
+    unlike neighbours (src/app_ising.cpp:88-95), = 2 + u/J."""
+    from scipy.special import ellipk
+    K2 = 1.0 / T  # 2 beta J
+    m = (1.0 - np.sinh(K2) ** -4) ** 0.125 if T < 1.0 / np.log(1 + np.sqrt(2)) else 0.0
+    k = 2.0 * np.sinh(K2) / np.cosh(K2) ** 2
+    u = -(1.0 / np.tanh(K2)) * (1.0 + (2.0 / np.pi) * (2.0 * np.tanh(K2) ** 2 - 1.0) * ellipk(k * k))
+    return m, 2.0 + u
+
+
+@pytest.mark.parametrize("T", [0.9, 1.0, 1.3, 1.6])
+def test_ising_2d_matches_onsager(T):
+    from spparks_b200 import LatticeSweep
+    L = 1024
+    s = LatticeSweep("ising", "sq/4n", L, L, 1, temperature=T, seed=2026)
+    s.upload(np.ones(L * L, dtype=np.int32))  # ordered start: no domain walls to anneal out
+    s.sweeps(0, 3000)
+    es, ms, sweep = [], [], 3000
+    for _ in range(60):
+        s.sweeps(sweep, 50)
+        sweep += 50
+        es.append(s.energy() / (L * L))
+        a = s.download()
+        ms.append(abs(2.0 * np.count_nonzero(a == 1) / a.size - 1.0))
+    m_exact, e_exact = onsager(T)
+    e, m = float(np.mean(es)), float(np.mean(ms))
+    # tolerance: 0.5 % of the energy scale / 0.005 in magnetisation (statistical error at
+    # L = 1024 over 60 samples is below 1e-3 away from T_c)
+    assert abs(e - e_exact) < 0.005 * max(e_exact, 0.2), (T, e, e_exact)
+    assert abs(m - m_exact) < 0.005 + (0.01 if m_exact == 0.0 else 0.0), (T, m, m_exact)
+
+
+def count_clusters_periodic(a):
+    """number of connected equal-spin clusters with the sc/26n neighbourhood and periodic wrap
+    (what diag_style cluster reports, src/diag_cluster.cpp:230-681): min-label propagation with
+    pointer jumping, on the GPU with torch (test infrastructure, not the product path)"""
+    import torch
+    L = a.shape[0]
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    lab = torch.arange(L ** 3, device="cuda").view(L, L, L)
+    dirs = [(x, y, z) for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1) if (x, y, z) != (0, 0, 0)]
+    while True:
+        new = lab
+        for d in dirs:
+            same = torch.roll(t, d, (0, 1, 2)) == t
+            new = torch.where(same, torch.minimum(new, torch.roll(lab, d, (0, 1, 2))), new)
+        flat = new.reshape(-1)
+        flat = flat[flat]  # a label is the index of a site of the same cluster
+        new = flat.view(L, L, L)
+        if torch.equal(new, lab):
+            break
+        lab = new
+    return int((lab.reshape(-1) == torch.arange(L ** 3, device="cuda")).sum().item())
+
+
+def test_potts_grain_growth_follows_reference_curve():
+    """potts/neighonly Q=10000 on sc/26n at T=0.5 from a random start: mean grain volume
+    N/ncluster and energy per site versus MCS against the unmodified reference (3 seeds of 96^3,
+    tests/golden/growth_reference.json).  North-star tolerance: 2 % on the mean grain size."""
+    from spparks_b200 import LatticeSweep
+    ref = json.load(open(os.path.join(GOLDEN, "growth_reference.json")))
+    L = 192  # 8x the reference volume: the GPU curve's own statistical error is below the reference's
+    s = LatticeSweep("potts/neighonly", "sc/26n", L, L, L, nspins=10000, temperature=0.5, seed=31337)
+    s.randomize(2024, 1, 10000)
+    done = 0
+    for sweeps, vol_ref, e_ref in zip(ref["sweeps"], ref["mean_grain_volume"], ref["energy_per_site"]):
+        s.sweeps(done, sweeps - done)
+        done = sweeps
+        e = s.energy() / L ** 3
+        assert abs(e - e_ref) < 0.01 * e_ref, (sweeps, e, e_ref)
+        if sweeps in ref["cluster_checkpoints"]:
+            a = s.download().reshape(L, L, L)
+            vol = L ** 3 / count_clusters_periodic(a)
+            assert abs(vol - vol_ref) < 0.02 * vol_ref, (sweeps, vol, vol_ref)
