@@ -13,6 +13,7 @@
 #include "../../include/spparks_cuda.h"
 #include "aux_kernels.cuh"
 #include "sweep_generic.cuh"
+#include "sweep_stream.cuh"
 #include "sweep_tiled.cuh"
 
 using namespace spk;
@@ -93,6 +94,9 @@ struct spk_cuda_handle {
   cudaEvent_t t0 = nullptr, t1 = nullptr, ev_halo = nullptr, ev_compute = nullptr;
   ncclComm_t comm = nullptr;
   bool tiled = true;  // tuned kernels allowed (SPK_CUDA_FORCE_GENERIC=1 disables, for A/B tests)
+  bool use_stream = true;  // SPK_CUDA_NO_STREAM=1 keeps the strip kernel (A/B tests)
+  bool stream_ok = false;  // TMA streaming kernel usable (3-D lattice, tensor map built)
+  CUtensorMap tmap;        // (x, y, plane incl. the two ghost planes) view of the slab
 };
 
 namespace {
@@ -172,6 +176,91 @@ int launch_generic(spk_cuda_handle *h, const SweepArgs &a) {
   return 0;
 }
 
+// TMA descriptor of the slab: int32 tensor (x, y, plane) whose plane 0 is the lower ghost plane.
+// cuTensorMapEncodeTiled is fetched through the runtime so that libcuda is not a link dependency.
+int build_tensor_map(spk_cuda_handle *h) {
+  h->stream_ok = false;
+  if (h->dim != 3 || h->nb != 1 || h->g.X % 4) return 0;
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    cudaGetLastError();
+    return 0;
+  }
+  const int rp = h->d.lattice == SPK_SC_26N ? StreamCfg<SPK_SC_26N>::RP : StreamCfg<SPK_SC_6N>::RP;
+  cuuint64_t dims[3] = {(cuuint64_t)h->g.X, (cuuint64_t)h->g.Y, (cuuint64_t)h->nslab + 2};
+  cuuint64_t strides[2] = {(cuuint64_t)h->g.X * 4, (cuuint64_t)h->g.X * h->g.Y * 4};
+  cuuint32_t box[3] = {(cuuint32_t)ST_BX, (cuuint32_t)rp, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ((encode_fn)fn)(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, h->base, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  h->stream_ok = (r == CUDA_SUCCESS);
+  return 0;
+}
+
+// periodic images of the slab dimension for a single-GPU run (the multi-GPU case is
+// spk_cuda_halo_exchange): ghost plane -1 <- last owned plane, ghost plane n <- first owned plane
+int refresh_ghosts_local(spk_cuda_handle *h) {
+  const size_t bytes = (size_t)h->plane * sizeof(int32_t);
+  CU(cudaMemcpyAsync(h->base, h->spin + (int64_t)(h->nslab - 1) * h->plane, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->spin + h->nlocal, h->spin, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  h->launches += 2;
+  return 0;
+}
+
+// returns 0 launched, -1 not applicable, >0 error
+template <int LAT, int MODEL>
+int launch_stream(spk_cuda_handle *h, const SweepArgs &a) {
+  if constexpr (LAT != SPK_SC_26N && LAT != SPK_SC_6N) {
+    return -1;
+  } else {
+    using C = StreamCfg<LAT>;
+    const Geo &g = a.g;
+    const Box &b = a.b;
+    if (!h->stream_ok || b.ilo != 0 || b.ihi != g.X || b.jlo != 0 || b.jhi != g.Y) return -1;
+    StreamMap sm;
+    const int c0 = a.c0;
+    int kfirst = b.klo, nq = b.khi - b.klo;
+    if (LAT == SPK_SC_26N) {
+      kfirst = b.klo + ((b.klo ^ (c0 >> 2)) & 1);
+      nq = kfirst < b.khi ? (b.khi - kfirst + 1) / 2 : 0;
+    }
+    if (nq <= 0) return 0;
+    sm.ntx = (g.X + ST_TX - 1) / ST_TX;
+    sm.nty = (g.Y + C::YT - 1) / C::YT;
+    sm.kfirst = kfirst;
+    sm.nq = nq;
+    const int grid_max = 2 * 148;
+    int nzc = (8 * grid_max + sm.ntx * sm.nty - 1) / (sm.ntx * sm.nty);
+    if (nzc > nq) nzc = nq;
+    if (nzc < 1) nzc = 1;
+    sm.qchunk = (nq + nzc - 1) / nzc;
+    sm.nzc = (nq + sm.qchunk - 1) / sm.qchunk;
+    sm.items = sm.ntx * sm.nty * sm.nzc;
+    const int grid = sm.items < grid_max ? sm.items : grid_max;
+    SweepArgs args = a;
+    if (h->d.nranks == 1) {  // the kernel reads the slab dimension through the ghost planes
+      if (refresh_ghosts_local(h)) return 1;
+      args.g.lo_wrap = -1;
+      args.g.hi_wrap = h->nslab;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(sweep_stream_kernel<LAT, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               C::SMEM_BYTES) != cudaSuccess)
+        return 1;
+      attr_set = true;
+    }
+    sweep_stream_kernel<LAT, MODEL><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, args, sm);
+    h->launches++;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  }
+}
+
 template <int LAT, int MODEL>
 int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
   SweepArgs a;
@@ -181,7 +270,10 @@ int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int
   h->nattempt += class_count<LAT>(h, a.b, a.c0) * nloop;
   if (rng == RNG_PHILOX) {
     if (h->tiled) {
-      int rc = launch_tiled<LAT, MODEL>(h->stream, a, &h->launches);
+      int rc = h->use_stream ? launch_stream<LAT, MODEL>(h, a) : -1;
+      if (rc == 0) return 0;
+      if (rc > 0) return fail("stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = launch_tiled<LAT, MODEL>(h->stream, a, &h->launches);
       if (rc == 0) return 0;
       if (rc > 0) return fail("tiled kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -292,6 +384,8 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
   h->nglobal = (int64_t)desc->nx * desc->ny * nz * h->nb;
   const char *fg = getenv("SPK_CUDA_FORCE_GENERIC");
   h->tiled = !(fg && fg[0] == '1');
+  const char *ns = getenv("SPK_CUDA_NO_STREAM");
+  h->use_stream = !(ns && ns[0] == '1');
   build_tables(h);
 
   auto cleanup = [&](int rc) { spk_cuda_destroy(h); return rc; };
@@ -302,6 +396,7 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
   }
   h->spin = h->base + h->plane;
   if (cudaMemset(h->base, 0, bytes) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
+  build_tensor_map(h);
   if (cudaMalloc(&h->naccept, 2 * sizeof(unsigned long long)) != cudaSuccess) return cleanup(fail("cudaMalloc failed"));
   h->escratch = h->naccept + 1;
   cudaMemset(h->naccept, 0, 2 * sizeof(unsigned long long));

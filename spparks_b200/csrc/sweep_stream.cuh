@@ -1,0 +1,281 @@
+// Streaming colour-set kernel for the 3-D lattices (sc/26n, sc/6n), Philox mode.
+//
+// Persistent CTAs walk work items = (x tile of 128 sites) x (y tile of 16 class rows) x (chunk of
+// class planes).  Inside an item a CTA streams along z: a ring of lattice planes lives in shared
+// memory, each plane brought in by ONE TMA box load (cp.async.bulk.tensor.3d, box = 136 x RP x 1
+// int32 = the tile plus a 4-element x halo chunk and a 1-row y halo on each side) that signals an
+// mbarrier; the planes of the next class plane are in flight while the current one is updated.
+// Every lattice plane is therefore read from L2/HBM once per tile instead of three times, loads
+// cost no issue slots, and the stencil windows are read from shared memory with immediate
+// offsets (one conflict-free LDS.128 + one LDS.32 per stencil row and thread).
+//
+// TMA zero-fills box elements outside the tensor; the periodic images that fall there (x and y
+// edges of the lattice only) are patched in shared memory with plain loads after the box has
+// landed.  The z direction never leaves the tensor: it includes the two ghost planes of the slab
+// (refreshed before each colour by spk_cuda_halo_exchange, also on a single GPU).
+#pragma once
+#include <cuda.h>
+#include "sweep_tiled.cuh"
+
+namespace spk {
+
+constexpr int ST_TX = 128;        // tile width in sites: 32 lanes x one 16-byte chunk
+constexpr int ST_BX = ST_TX + 8;  // TMA box inner extent
+constexpr int ST_CR = 16;         // class rows per tile: 8 warps x 2
+
+template <int LAT> struct StreamCfg {
+  static constexpr int JSTEP = (LAT == SPK_SC_26N) ? 2 : 1;  // class rows / planes are every
+  static constexpr int KSTEP = (LAT == SPK_SC_26N) ? 2 : 1;  // JSTEP-th row / KSTEP-th plane
+  static constexpr int YT = ST_CR * JSTEP;                   // lattice rows per tile
+  static constexpr int RP = YT + 2;                          // rows per plane in smem (y halo)
+  static constexpr int RING = 3 + KSTEP;                     // stencil window + planes in flight
+  static constexpr int PLANE_BYTES = ST_BX * RP * 4;
+  static constexpr int PLANE_STRIDE = (PLANE_BYTES + 127) / 128 * 128;
+  static constexpr int SMEM_BYTES = RING * PLANE_STRIDE + 8 * RING;
+};
+
+struct StreamMap {
+  int ntx, nty, nzc, items;  // tiles in x, y; plane chunks; ntx*nty*nzc
+  int kfirst, nq, qchunk;    // first class plane (local index), class planes, class planes per item
+};
+
+// ---- mbarrier / TMA wrappers (PTX ISA: mbarrier, cp.async.bulk.tensor) ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+// Periodic images of the halo cells of one smem plane that fall outside the lattice in x or y.
+// Only cells the stencil can touch are patched: column x0-1, the first column past the tile (or
+// past the row end), row y0-1 and the first row past the lattice.  Threads 0..RP-1 own one row of
+// the two columns, threads 64..64+BX-1 one column of the two rows; the loads are issued early
+// (when the TMA box is issued) and stored once the box has landed.
+struct PatchPlan {
+  int col_l, col_r;  // smem column to patch on the left / right, or -1
+  int row_t, row_b;  // smem row to patch at the top (y = -1) / bottom (y = Y), or -1
+  int gx_l, gx_r;    // lattice x of the periodic images of those columns
+};
+
+template <int LAT>
+__device__ __forceinline__ PatchPlan make_patch_plan(int x0, int y0, int rowlen, int Y) {
+  using C = StreamCfg<LAT>;
+  PatchPlan pp;
+  pp.col_l = x0 == 0 ? 3 : -1;
+  pp.gx_l = rowlen - 1;
+  const int past = rowlen - x0;  // tile-relative x of the first column past the row end
+  pp.col_r = past <= ST_TX ? 4 + past : -1;
+  pp.gx_r = 0;
+  pp.row_t = y0 == 0 ? 0 : -1;
+  const int rb = Y - y0 + 1;
+  pp.row_b = rb <= C::RP - 1 ? rb : -1;
+  return pp;
+}
+
+template <int LAT>
+__device__ __forceinline__ void patch_load(const PatchPlan &pp, const int32_t *gplane, int x0, int y0, int rowlen,
+                                           int Y, int tid, int (&v)[2]) {
+  using C = StreamCfg<LAT>;
+  v[0] = v[1] = 0;
+  if (tid < C::RP) {  // my row of the two columns
+    int y = y0 - 1 + tid;
+    y = y < 0 ? Y - 1 : (y >= Y ? y - Y : y);
+    if (y < Y) {
+      const int32_t *row = gplane + (long long)y * rowlen;
+      if (pp.col_l >= 0) v[0] = row[pp.gx_l];
+      if (pp.col_r >= 0) v[1] = row[pp.gx_r];
+    }
+  } else if (tid >= 64 && tid < 64 + ST_BX) {  // my column of the two rows
+    int x = x0 - 4 + (tid - 64);
+    x = x < 0 ? x + rowlen : (x >= rowlen ? x - rowlen : x);
+    if (x >= 0 && x < rowlen) {
+      if (pp.row_t >= 0) v[0] = gplane[(long long)(Y - 1) * rowlen + x];
+      if (pp.row_b >= 0) v[1] = gplane[x];
+    }
+  }
+}
+
+template <int LAT>
+__device__ __forceinline__ void patch_store(const PatchPlan &pp, int32_t *pl, int tid, const int (&v)[2]) {
+  using C = StreamCfg<LAT>;
+  if (tid < C::RP) {
+    if (pp.col_l >= 0) pl[tid * ST_BX + pp.col_l] = v[0];
+    if (pp.col_r >= 0) pl[tid * ST_BX + pp.col_r] = v[1];
+  } else if (tid >= 64 && tid < 64 + ST_BX) {
+    if (pp.row_t >= 0) pl[pp.row_t * ST_BX + (tid - 64)] = v[0];
+    if (pp.row_b >= 0) pl[pp.row_b * ST_BX + (tid - 64)] = v[1];
+  }
+}
+
+// one class row of one class plane: the thread's 16-byte chunk holds two class sites at P, P+2
+template <int LAT, int MODEL, int P>
+__device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *const (&pl)[3], int r, int lane,
+                                            int32_t *gchunk, unsigned long long gsite0) {
+  using L = Lat<LAT>;
+  constexpr int NN = L::NN;
+  using R = RowInfo<LAT, 0>;
+  // W[row][1 + e] = element e of the chunk, e in [-1, 4]
+  int W[9][6];
+  static_for<9>([&](auto RR) {
+    constexpr int rr = decltype(RR)::value, dy = rr % 3 - 1, dz = rr / 3 - 1;
+    if constexpr (R::used(dy, dz)) {
+      const int32_t *rowp = pl[dz + 1] + (r + dy) * ST_BX + 4 + 4 * lane;
+      const int4 t = *reinterpret_cast<const int4 *>(rowp);
+      W[rr][1] = t.x; W[rr][2] = t.y; W[rr][3] = t.z; W[rr][4] = t.w;
+      if constexpr (P == 0 && R::dmin(dy, dz) < 0) W[rr][0] = rowp[-1];
+      if constexpr (P == 1 && R::dmax(dy, dz) > 0) W[rr][5] = rowp[4];
+    }
+  });
+
+  int cur[2] = {W[4][1 + P], W[4][3 + P]};
+  const int before0 = cur[0], before1 = cur[1];
+  int accepted = 0;
+  const unsigned long long leader = gsite0 + P;
+  for (int l = 0; l < a.nloop; l++) {
+    const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep,
+                                    (uint32_t)l * 16u + (uint32_t)(a.c0 + 1), a.ev.k0, a.ev.k1);
+    static_for<2>([&](auto H) {
+      constexpr int h = decltype(H)::value, e = P + 2 * h;
+      int v[NN];
+      static_for<NN>([&](auto N_) {
+        constexpr int n = decltype(N_)::value;
+        constexpr Off o = L::off(0, n);
+        v[n] = W[(o.dz + 1) * 3 + (o.dy + 1)][1 + e + o.dx];
+      });
+      Draws<RNG_PHILOX> d;
+      d.w1 = h ? blk.z : blk.x;
+      d.w2 = h ? blk.w : blk.y;
+      const int nw = site_event<MODEL, RNG_PHILOX, NN>(a.ev, cur[h], v, d);
+      accepted += (nw != cur[h]);
+      cur[h] = nw;
+    });
+  }
+  if (cur[0] != before0 || cur[1] != before1) {
+    W[4][1 + P] = cur[0];
+    W[4][3 + P] = cur[1];
+    *reinterpret_cast<int4 *>(gchunk) = make_int4(W[4][1], W[4][2], W[4][3], W[4][4]);
+  }
+  return accepted;
+}
+
+template <int LAT, int MODEL>
+__global__ void __launch_bounds__(256, 2)
+sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SweepArgs a,
+                    const __grid_constant__ StreamMap sm) {
+  using C = StreamCfg<LAT>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + C::RING * C::PLANE_STRIDE);
+  auto plane_ptr = [&](uint32_t seq) { return reinterpret_cast<int32_t *>(smem_raw + (seq % C::RING) * C::PLANE_STRIDE); };
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Geo &g = a.g;
+  const int rowlen = g.X, Y = g.Y;
+  const long long sy = rowlen, sz = sy * Y;
+
+  if (tid == 0) {
+    for (int i = 0; i < C::RING; i++) mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int kk, uint32_t seq, int x0, int y0) {  // plane kk (local, -1..Z) as sequence number seq
+    uint64_t *bar = &full[seq % C::RING];
+    mbar_expect_tx(bar, C::PLANE_BYTES);
+    tma_load_3d(plane_ptr(seq), &tmap, bar, x0 - 4, y0 - 1, kk + 1);  // tensor plane 0 = lower ghost plane
+  };
+  auto wait = [&](uint32_t seq) { mbar_wait(&full[seq % C::RING], (seq / C::RING) & 1u); };
+
+  uint32_t Q = 0;  // running plane sequence number: slot = Q % RING, barrier parity = (Q / RING) & 1
+  int accepted = 0;
+  for (int item = blockIdx.x; item < sm.items; item += gridDim.x) {
+    const int tx = item % sm.ntx, ty = (item / sm.ntx) % sm.nty, zc = item / (sm.ntx * sm.nty);
+    const int x0 = tx * ST_TX, y0 = ty * C::YT;
+    const int q0 = zc * sm.qchunk, q1 = min(q0 + sm.qchunk, sm.nq), nsteps = q1 - q0;
+    const int kstart = sm.kfirst + q0 * C::KSTEP;
+    const bool edge = x0 == 0 || x0 + ST_TX >= rowlen || y0 == 0 || y0 + C::YT >= Y;
+
+    const PatchPlan pp = make_patch_plan<LAT>(x0, y0, rowlen, Y);
+
+    if (tid == 0)
+      for (int p = 0; p < 3; p++) issue(kstart - 1 + p, Q + p, x0, y0);
+    if (edge) {  // prologue: the three planes of the first stencil window
+      int pv0[3][2];
+      for (int p = 0; p < 3; p++)
+        patch_load<LAT>(pp, a.spin + (long long)(kstart - 1 + p) * sz, x0, y0, rowlen, Y, tid, pv0[p]);
+      for (int p = 0; p < 3; p++) {
+        wait(Q + p);
+        patch_store<LAT>(pp, plane_ptr(Q + p), tid, pv0[p]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
+
+    int pv[C::KSTEP][2];  // patch values of the planes in flight
+    for (int s = 0; s < nsteps; s++) {
+      const int k = kstart + s * C::KSTEP;
+      const uint32_t Qs = Q + s * C::KSTEP;  // sequence number of plane k-1
+
+      if (s > 0) {  // planes k .. k+KSTEP-1 shifted into the window: wait, then patch
+        for (int p = 0; p < C::KSTEP; p++) wait(Qs + 3 - C::KSTEP + p);
+        if (edge) {
+          for (int p = 0; p < C::KSTEP; p++) patch_store<LAT>(pp, plane_ptr(Qs + 3 - C::KSTEP + p), tid, pv[p]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncthreads();
+        }
+      } else if (!edge) {
+        for (int p = 0; p < 3; p++) wait(Qs + p);
+      }
+
+      if (s + 1 < nsteps) {  // next step's planes: TMA boxes and (edge tiles) their patch loads
+        if (tid == 0)
+          for (int p = 0; p < C::KSTEP; p++) issue(k + 2 + p, Qs + 3 + p, x0, y0);
+        if (edge)
+          for (int p = 0; p < C::KSTEP; p++)
+            patch_load<LAT>(pp, a.spin + (long long)(k + 2 + p) * sz, x0, y0, rowlen, Y, tid, pv[p]);
+      }
+
+      const int32_t *const pl[3] = {plane_ptr(Qs), plane_ptr(Qs + 1), plane_ptr(Qs + 2)};
+      const int x = x0 + 4 * lane;
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        const int cr = warp + 8 * t;
+        int y, px;
+        if constexpr (LAT == SPK_SC_26N) {
+          y = y0 + 2 * cr + ((a.c0 >> 1) & 1);
+          px = a.c0 & 1;
+        } else {
+          y = y0 + cr;
+          px = (a.c0 + y + k + g.g0) & 1;
+        }
+        if (y < Y && x < rowlen) {  // y: warp-uniform
+          const int r = y - y0 + 1;
+          int32_t *gchunk = a.spin + (long long)k * sz + (long long)y * sy + x;
+          const unsigned long long gsite0 =
+              ((unsigned long long)(k + g.g0) * g.gY + y) * (unsigned long long)g.gX + x;
+          if (px) accepted += stream_chunk<LAT, MODEL, 1>(a, pl, r, lane, gchunk, gsite0);
+          else accepted += stream_chunk<LAT, MODEL, 0>(a, pl, r, lane, gchunk, gsite0);
+        }
+      }
+      __syncthreads();  // planes k-1 (and k) may now be overwritten by the next step's loads
+    }
+    Q += 3 + (nsteps - 1) * C::KSTEP;
+  }
+  accepted = __reduce_add_sync(0xffffffffu, accepted);
+  if (lane == 0 && accepted) atomicAdd(a.naccept, (unsigned long long)accepted);
+}
+
+}  // namespace spk

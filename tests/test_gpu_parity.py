@@ -102,16 +102,23 @@ CASES = [
     ("potts/neighonly", "tri", (20, 16, 1), 5, 0.4),
     ("potts/neighonly", "sq/4n", (24, 24, 1), 3, 0.9),
     ("potts/pin", "sc/26n", (48, 10, 6), 50, 0.5),
+    # several x/y tiles and plane chunks of the streaming kernel, ragged tile edges
+    ("potts", "sc/26n", (272, 70, 40), 30, 0.7),
+    ("potts", "sc/6n", (260, 40, 18), 5, 0.9),
+    ("potts/neighonly", "sc/26n", (132, 34, 12), 40, 0.5),
 ]
 
 
 @pytest.mark.parametrize("model,lat,n,q,T", CASES, ids=lambda v: str(v).replace(" ", ""))
-@pytest.mark.parametrize("force_generic", [False, True], ids=["tuned", "generic"])
-def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, force_generic, monkeypatch):
-    """Production (Philox) mode, three full sweeps, both the tuned and the generic kernels:
-    bit-exact against the oracle evaluating the same counter-based stream."""
-    if force_generic:
+@pytest.mark.parametrize("kernel", ["tuned", "strip", "generic"])
+def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, kernel, monkeypatch):
+    """Production (Philox) mode, three full sweeps, through every kernel family (TMA streaming
+    kernel where it applies, strip kernel, generic kernel): bit-exact against the oracle
+    evaluating the same counter-based stream."""
+    if kernel == "generic":
         monkeypatch.setenv("SPK_CUDA_FORCE_GENERIC", "1")
+    if kernel == "strip":
+        monkeypatch.setenv("SPK_CUDA_NO_STREAM", "1")
     rng = np.random.default_rng(7)
     o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
     spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=o.nsites, dtype=np.int32)
