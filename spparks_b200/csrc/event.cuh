@@ -136,6 +136,28 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
     }
   }
 
+  // e0 == NN (every neighbour unlike): efinal <= einitial whatever the trial, so the event is
+  // accepted without counting; a warp whose lanes all sit in that case (fresh random lattices)
+  // skips the second energy altogether
+  if constexpr (NN > 8) {
+    if (e0 == NN) return trial;
+  }
+  if constexpr (MODEL == SPK_ISING) {
+    // two-state shortcut: with spins in {1,2} the neighbours unlike `old` are exactly the ones
+    // like a different trial, so efinal = NN - einitial and no second count is needed
+    if (trial == old) return old;
+    const int dE2 = NN - 2 * e0;
+    if (dE2 <= 0) return trial;
+    if (p.t_zero) return old;
+    if constexpr (RNG == RNG_PHILOX) {
+      return d.w2 > p.thr[dE2] ? old : trial;
+    } else {
+      double u;
+      if constexpr (RNG == RNG_INJECTED) u = d.u2;
+      else u = park_uniform(d.seed);
+      return u > p.ptab[dE2] ? old : trial;
+    }
+  }
   const int e1 = unlike<NN>(v, trial, p.one);
   if (e1 <= e0) return trial;
   if (p.t_zero) return old;

@@ -14,6 +14,7 @@
 #include "aux_kernels.cuh"
 #include "sweep_generic.cuh"
 #include "sweep_stream.cuh"
+#include "sweep_tile2d.cuh"
 #include "sweep_tiled.cuh"
 
 using namespace spk;
@@ -83,6 +84,9 @@ struct spk_cuda_handle {
   Geo g;
   int64_t nlocal, nglobal, plane;  // plane = elements of one plane (3-D) / row (2-D) of the slab dimension
   int nslab;                       // local extent along the slab dimension
+  int gh = 1;                      // ghost planes / rows on each side of the slab
+  bool fused2d_ok = false;         // colour-fused 2-D tile kernel usable (tensor map built)
+  bool use_fused = true;           // SPK_CUDA_NO_FUSED=1 keeps the per-colour kernels (A/B tests)
   int32_t *base = nullptr;         // allocation incl. ghost planes
   int32_t *spin = nullptr;         // first owned site
   double *u1 = nullptr, *u2 = nullptr;
@@ -180,7 +184,9 @@ int launch_generic(spk_cuda_handle *h, const SweepArgs &a) {
 // cuTensorMapEncodeTiled is fetched through the runtime so that libcuda is not a link dependency.
 int build_tensor_map(spk_cuda_handle *h) {
   h->stream_ok = false;
-  if (h->dim != 3 || h->nb != 1 || h->g.X % 4) return 0;
+  h->fused2d_ok = false;
+  if (h->dim == 3 && (h->nb != 1 || h->g.X % 4)) return 0;
+  if (h->dim == 2 && (h->g.X * h->nb) % 8) return 0;
   typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -188,6 +194,19 @@ int build_tensor_map(spk_cuda_handle *h) {
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
     cudaGetLastError();
+    return 0;
+  }
+  if (h->dim == 2) {  // (element, row) view of the slab, row 0 = lowest ghost row
+    const int bh = h->d.lattice == SPK_SQ_4N ? Tile2dCfg<SPK_SQ_4N>::BH
+                   : h->d.lattice == SPK_SQ_8N ? Tile2dCfg<SPK_SQ_8N>::BH : Tile2dCfg<SPK_TRI>::BH;
+    cuuint64_t dims[2] = {(cuuint64_t)h->plane, (cuuint64_t)h->nslab + 2 * h->gh};
+    cuuint64_t strides[1] = {(cuuint64_t)h->plane * 4};
+    cuuint32_t box[2] = {(cuuint32_t)T2_BW, (cuuint32_t)bh};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((encode_fn)fn)(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, h->base, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    h->fused2d_ok = (r == CUDA_SUCCESS);
     return 0;
   }
   const int rp = h->d.lattice == SPK_SC_26N ? StreamCfg<SPK_SC_26N>::RP : StreamCfg<SPK_SC_6N>::RP;
@@ -206,10 +225,80 @@ int build_tensor_map(spk_cuda_handle *h) {
 // spk_cuda_halo_exchange): ghost plane -1 <- last owned plane, ghost plane n <- first owned plane
 int refresh_ghosts_local(spk_cuda_handle *h) {
   const size_t bytes = (size_t)h->plane * sizeof(int32_t);
-  CU(cudaMemcpyAsync(h->base, h->spin + (int64_t)(h->nslab - 1) * h->plane, bytes, cudaMemcpyDeviceToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->spin + h->nlocal, h->spin, bytes, cudaMemcpyDeviceToDevice, h->stream));
-  h->launches += 2;
+  if (h->nslab >= h->gh) {
+    CU(cudaMemcpyAsync(h->base, h->spin + (int64_t)(h->nslab - h->gh) * h->plane, bytes * h->gh,
+                       cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->spin + h->nlocal, h->spin, bytes * h->gh, cudaMemcpyDeviceToDevice, h->stream));
+    h->launches += 2;
+    return 0;
+  }
+  for (int m = 1; m <= h->gh; m++) {  // slab thinner than the ghost depth: images wrap more than once
+    const int lo = ((h->nslab - m) % h->nslab + h->nslab) % h->nslab, hi = (m - 1) % h->nslab;
+    CU(cudaMemcpyAsync(h->spin - (int64_t)m * h->plane, h->spin + (int64_t)lo * h->plane, bytes,
+                       cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->spin + h->nlocal + (int64_t)(m - 1) * h->plane, h->spin + (int64_t)hi * h->plane, bytes,
+                       cudaMemcpyDeviceToDevice, h->stream));
+    h->launches += 2;
+  }
   return 0;
+}
+
+// whole colour-fused sweep of a 2-D lattice; returns 0 launched, -1 not applicable, >0 error
+template <int LAT, int MODEL>
+int launch_tile2d(spk_cuda_handle *h, const SweepArgs &a) {
+  if constexpr (Lat<LAT>::DIM != 2) {
+    return -1;
+  } else {
+    using C = Tile2dCfg<LAT>;
+    if (!h->fused2d_ok) return -1;
+    const int rowlen = h->g.X * Lat<LAT>::NB;
+    Tile2dMap tm;
+    tm.ntx = (rowlen + C::OW - 1) / C::OW;
+    tm.nty = (h->nslab + T2_OH - 1) / T2_OH;
+    tm.items = tm.ntx * tm.nty;
+    tm.gh = h->gh;
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(sweep_tile2d_kernel<LAT, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               C::SMEM_BYTES) != cudaSuccess)
+        return 1;
+      attr_set = true;
+    }
+    const int grid_max = 2 * 148;
+    const int grid = tm.items < grid_max ? tm.items : grid_max;
+    sweep_tile2d_kernel<LAT, MODEL><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, a, tm);
+    h->launches++;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  }
+}
+
+template <int LAT> int fused_sweep_l(spk_cuda_handle *h, const SweepArgs &a) {
+  switch (h->d.model) {
+    case SPK_ISING: return launch_tile2d<LAT, SPK_ISING>(h, a);
+    case SPK_POTTS: return launch_tile2d<LAT, SPK_POTTS>(h, a);
+    case SPK_POTTS_NEIGHONLY: return launch_tile2d<LAT, SPK_POTTS_NEIGHONLY>(h, a);
+    case SPK_POTTS_PIN: return launch_tile2d<LAT, SPK_POTTS_PIN>(h, a);
+  }
+  return -1;
+}
+
+// one whole sweep (all colours) in one launch where a fused kernel exists: 0 done, -1 not applicable
+int fused_sweep(spk_cuda_handle *h) {
+  if (!h->tiled || !h->use_fused || h->dim != 2 || !h->fused2d_ok) return -1;
+  SweepArgs a;
+  a.spin = h->spin; a.g = h->g; a.c0 = 0; a.nloop = 1; a.ev = h->ev;
+  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept;
+  a.b = Box{0, h->g.X, 0, h->g.Y, 0, 1};
+  if (h->d.nranks == 1 && refresh_ghosts_local(h)) return 1;
+  int rc;
+  switch (h->d.lattice) {
+    case SPK_SQ_4N: rc = fused_sweep_l<SPK_SQ_4N>(h, a); break;
+    case SPK_SQ_8N: rc = fused_sweep_l<SPK_SQ_8N>(h, a); break;
+    case SPK_TRI: rc = fused_sweep_l<SPK_TRI>(h, a); break;
+    default: rc = -1;
+  }
+  if (rc == 0) h->nattempt += h->nlocal;
+  return rc;
 }
 
 // returns 0 launched, -1 not applicable, >0 error
@@ -386,15 +475,25 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
   h->tiled = !(fg && fg[0] == '1');
   const char *ns = getenv("SPK_CUDA_NO_STREAM");
   h->use_stream = !(ns && ns[0] == '1');
+  const char *nf = getenv("SPK_CUDA_NO_FUSED");
+  h->use_fused = !(nf && nf[0] == '1');
   build_tables(h);
 
   auto cleanup = [&](int rc) { spk_cuda_destroy(h); return rc; };
-  const size_t bytes = (size_t)(h->nlocal + 2 * h->plane) * sizeof(int32_t);
+  // 2-D slabs keep T2_GH ghost rows per side: the colour-fused tile kernel needs one row per
+  // fused colour step; 3-D slabs one plane (delpropensity = 1)
+  h->gh = dim == 2 ? T2_GH : 1;
+  if (desc->nranks > 1 && h->nslab < h->gh) {
+    const int gh = h->gh;
+    delete h;
+    return fail("slab thinner than its %d ghost layers", gh);
+  }
+  const size_t bytes = (size_t)(h->nlocal + 2 * (int64_t)h->gh * h->plane) * sizeof(int32_t);
   if (cudaMalloc(&h->base, bytes) != cudaSuccess) {
     cudaGetLastError();
     return cleanup(fail("cudaMalloc of %zu bytes for the lattice failed", bytes));
   }
-  h->spin = h->base + h->plane;
+  h->spin = h->base + (int64_t)h->gh * h->plane;
   if (cudaMemset(h->base, 0, bytes) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
   build_tensor_map(h);
   if (cudaMalloc(&h->naccept, 2 * sizeof(unsigned long long)) != cudaSuccess) return cleanup(fail("cudaMalloc failed"));
@@ -538,8 +637,8 @@ int spk_cuda_halo_exchange(spk_cuda_handle *h) {
   if (!h->comm) return fail("spk_cuda_comm_init has not been called");
   CU(cudaSetDevice(h->d.device));
   const int lower = (h->d.rank + h->d.nranks - 1) % h->d.nranks, upper = (h->d.rank + 1) % h->d.nranks;
-  const size_t n = (size_t)h->plane;
-  int32_t *first = h->spin, *last = h->spin + (int64_t)(h->nslab - 1) * h->plane;
+  const size_t n = (size_t)h->plane * h->gh;  // gh layers per side
+  int32_t *first = h->spin, *last = h->spin + (int64_t)(h->nslab - h->gh) * h->plane;
   int32_t *ghost_lo = h->base, *ghost_hi = h->spin + h->nlocal;
   // the exchange runs on the compute stream's timeline: it must see the previous colour's
   // writes and the next colour kernel must see the ghosts
@@ -556,8 +655,17 @@ int spk_cuda_halo_exchange(spk_cuda_handle *h) {
 int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
   if (!h) return fail("null handle");
   if (nsweeps < 0) return fail("nsweeps must be >= 0");
+  CU(cudaSetDevice(h->d.device));
   for (int s = 0; s < nsweeps; s++) {
     h->ev.sweep = first_sweep + (uint32_t)s;
+    if (h->tiled && h->use_fused && h->dim == 2 && h->fused2d_ok) {
+      // 2-D: one launch per sweep; ghost rows (one per fused colour step) are refreshed once
+      int rc = spk_cuda_halo_exchange(h);
+      if (rc) return rc;
+      rc = fused_sweep(h);
+      if (rc == 0) continue;
+      if (rc > 0) return fail("fused sweep launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     for (int color = 1; color <= h->nc; color++) {
       int rc = spk_cuda_halo_exchange(h);
       if (rc) return rc;

@@ -106,6 +106,13 @@ CASES = [
     ("potts", "sc/26n", (272, 70, 40), 30, 0.7),
     ("potts", "sc/6n", (260, 40, 18), 5, 0.9),
     ("potts/neighonly", "sc/26n", (132, 34, 12), 40, 0.5),
+    # several tiles of the colour-fused 2-D kernel (interior 240 x 64), ragged edges, short rows
+    ("ising", "sq/4n", (496, 130, 1), 2, 1.1346),
+    ("ising", "sq/4n", (8, 6, 1), 2, 1.5),
+    ("potts", "sq/8n", (264, 70, 1), 6, 0.7),
+    ("potts", "tri", (252, 66, 1), 9, 0.5),
+    ("potts/neighonly", "tri", (124, 10, 1), 4, 0.6),
+    ("potts/pin", "sq/8n", (128, 64, 1), 8, 0.8),
 ]
 
 
@@ -119,6 +126,7 @@ def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, kernel, monkeypa
         monkeypatch.setenv("SPK_CUDA_FORCE_GENERIC", "1")
     if kernel == "strip":
         monkeypatch.setenv("SPK_CUDA_NO_STREAM", "1")
+        monkeypatch.setenv("SPK_CUDA_NO_FUSED", "1")
     rng = np.random.default_rng(7)
     o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
     spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=o.nsites, dtype=np.int32)
