@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 
 #include "../../include/spparks_cuda.h"
 #include "aux_kernels.cuh"
@@ -101,6 +102,8 @@ struct spk_cuda_handle {
   bool use_stream = true;  // SPK_CUDA_NO_STREAM=1 keeps the strip kernel (A/B tests)
   bool stream_ok = false;  // TMA streaming kernel usable (3-D lattice, tensor map built)
   CUtensorMap tmap;        // (x, y, plane incl. the two ghost planes) view of the slab
+  int32_t *base_alt = nullptr;  // second lattice buffer of the out-of-place fused 2-D sweep
+  CUtensorMap tmap_alt;
 };
 
 namespace {
@@ -206,7 +209,11 @@ int build_tensor_map(spk_cuda_handle *h) {
     CUresult r = ((encode_fn)fn)(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, h->base, dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    h->fused2d_ok = (r == CUDA_SUCCESS);
+    if (r == CUDA_SUCCESS && h->base_alt)
+      r = ((encode_fn)fn)(&h->tmap_alt, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, h->base_alt, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    h->fused2d_ok = (r == CUDA_SUCCESS && h->base_alt);
     return 0;
   }
   const int rp = h->d.lattice == SPK_SC_26N ? StreamCfg<SPK_SC_26N>::RP : StreamCfg<SPK_SC_6N>::RP;
@@ -264,11 +271,17 @@ int launch_tile2d(spk_cuda_handle *h, const SweepArgs &a) {
         return 1;
       attr_set = true;
     }
-    const int grid_max = 2 * 148;
+    const int grid_max = 3 * 148;
     const int grid = tm.items < grid_max ? tm.items : grid_max;
-    sweep_tile2d_kernel<LAT, MODEL><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, a, tm);
+    int32_t *dst = h->base_alt + (int64_t)h->gh * h->plane;
+    sweep_tile2d_kernel<LAT, MODEL><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, a, tm, dst);
     h->launches++;
-    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    if (cudaGetLastError() != cudaSuccess) return 1;
+    // the destination becomes the lattice (stream order makes this safe for later launches)
+    std::swap(h->base, h->base_alt);
+    std::swap(h->tmap, h->tmap_alt);
+    h->spin = h->base + (int64_t)h->gh * h->plane;
+    return 0;
   }
 }
 
@@ -495,6 +508,15 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
   }
   h->spin = h->base + (int64_t)h->gh * h->plane;
   if (cudaMemset(h->base, 0, bytes) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
+  if (dim == 2 && h->tiled && h->use_fused && (h->plane % 8) == 0) {
+    // destination buffer of the out-of-place colour-fused sweep (2-D lattices only)
+    if (cudaMalloc(&h->base_alt, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      h->base_alt = nullptr;  // not fatal: the per-colour kernels need no second buffer
+    } else if (cudaMemset(h->base_alt, 0, bytes) != cudaSuccess) {
+      return cleanup(fail("cudaMemset failed"));
+    }
+  }
   build_tensor_map(h);
   if (cudaMalloc(&h->naccept, 2 * sizeof(unsigned long long)) != cudaSuccess) return cleanup(fail("cudaMalloc failed"));
   h->escratch = h->naccept + 1;
@@ -515,7 +537,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  cudaFree(h->base); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
+  cudaFree(h->base); cudaFree(h->base_alt); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);

@@ -9,6 +9,9 @@
 // produce.  Halo sites are updated redundantly by the neighbouring tiles with the same result,
 // because the random stream is keyed on (seed, global site, sweep, colour) and not on who computes.
 // Traffic: 8 B per site and sweep (+ halo) instead of the 4*(C+1) B of the per-colour kernels.
+// The sweep is out of place (source lattice -> destination lattice, swapped by the host after the
+// launch): a tile's halo must hold PRE-sweep spins, which an in-place store of a neighbouring
+// tile's interior would destroy.
 //
 // Inside a colour step each warp marches down its band of rows keeping the three stencil rows of
 // its 8-element strips in registers, so a row is read from shared memory once per colour.
@@ -103,9 +106,9 @@ __device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t 
 }
 
 template <int LAT, int MODEL>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 sweep_tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SweepArgs a,
-                    const __grid_constant__ Tile2dMap tm) {
+                    const __grid_constant__ Tile2dMap tm, int32_t *__restrict__ dst) {
   using L = Lat<LAT>;
   using C = Tile2dCfg<LAT>;
   constexpr int NB = L::NB;
@@ -158,8 +161,8 @@ sweep_tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       const int ylo = c0 + 1, yhi = C::BH - c0 - 1;
       const int xlo = C::RX * (c0 + 1), xhi = T2_BW - C::RX * (c0 + 1);
       // this warp's band of rows
-      const int nrow = yhi - ylo, per = (nrow + 7) / 8;
-      const int y0 = ylo + warp * per, y1 = min(y0 + per, yhi);
+      const int nrow = yhi - ylo;
+      const int y0 = ylo + (warp * nrow) / 8, y1 = ylo + ((warp + 1) * nrow) / 8;
       // lanes 1..30 hold strips that are valid in every step (RX*C <= 8); lane 0 / 31 hold the halo
       // strips, of which only the sites inside [xlo, xhi) may still be updated
       const int p_lo = lane == 0 ? xlo : 0, p_hi = lane == 31 ? xhi - (T2_BW - 8) : 8;
@@ -217,7 +220,7 @@ sweep_tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       const int r = c / CPR, q = c - r * CPR;
       const int yrow = yo + r, x = xo + 4 * q;
       if (yrow < Y && x < rowlen)
-        *reinterpret_cast<int4 *>(a.spin + (long long)yrow * rowlen + x) =
+        *reinterpret_cast<int4 *>(dst + (long long)yrow * rowlen + x) =
             *reinterpret_cast<const int4 *>(tile + (C::HY + r) * T2_BW + C::HX + 4 * q);
     }
     __syncthreads();  // the tile buffer is reused by the next item

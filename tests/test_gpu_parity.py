@@ -212,3 +212,25 @@ def test_device_randomize_distribution():
     assert a.min() == 1 and a.max() == 100
     counts = np.bincount(a, minlength=101)[1:]
     assert abs(counts - a.size / 100).max() < 6 * np.sqrt(a.size / 100)
+
+
+@pytest.mark.parametrize("model,lat,n,q,T", [
+    ("ising", "sq/4n", (4096, 2048, 1), 2, 1.1346),     # 576 tiles of the fused 2-D kernel: more than are resident
+    ("potts", "tri", (2048, 1280, 1), 50, 0.5),
+    ("potts", "sc/26n", (256, 160, 96), 200, 0.6),      # 40 plane chunks x 10 tiles of the streaming kernel
+], ids=["ising-sq4n", "potts-tri", "potts-sc26n"])
+def test_large_lattices_bit_exact_vs_oracle(model, lat, n, q, T):
+    """Lattices with more tiles than resident CTAs, so that tiles are loaded after other tiles have
+    already been stored (catches in-place halo hazards that small lattices cannot show)."""
+    rng = np.random.default_rng(21)
+    o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
+    spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=o.nsites, dtype=np.int32)
+    s = _sweep(model, lat, n, q, T, seed=777)
+    s.upload(spins)
+    want = spins.copy()
+    nacc = 0
+    for sw in range(2):
+        nacc += o.sweep_philox(want, 777, sw)
+    s.sweeps(0, 2)
+    assert np.array_equal(s.download(), want)
+    assert s.counters() == (nacc, 2 * o.nsites)
