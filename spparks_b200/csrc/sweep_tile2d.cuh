@@ -54,8 +54,8 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 
 // one 8-element strip of one row for colour step c0; P = offset of the first class site
 template <int LAT, int MODEL, int P>
-__device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t *tile, int yl, int e0, int (&W)[3][16],
-                                            unsigned long long grow, bool count, int p_lo, int p_hi) {
+__device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t *own, const int (&Wm)[16], int (&Wc)[16],
+                                            const int (&Wp)[16], unsigned long long grow, bool count) {
   using L = Lat<LAT>;
   constexpr int NN = L::NN, NB = L::NB;
   constexpr int S = 2 * NB, NS = 8 / S;
@@ -64,7 +64,7 @@ __device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t 
   int cur[NS], before[NS];
   static_for<NS>([&](auto S_) {
     constexpr int s = decltype(S_)::value;
-    before[s] = cur[s] = W[1][4 + P + S * s];
+    before[s] = cur[s] = Wc[4 + P + S * s];
   });
   int accepted = 0;
   static_for<NS / 2>([&](auto PR) {
@@ -78,29 +78,28 @@ __device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t 
       static_for<NN>([&](auto N_) {
         constexpr int n = decltype(N_)::value;
         constexpr Off o = L::off(M, n);
-        v[n] = W[o.dy + 1][4 + p + R::delta(n)];
+        v[n] = (o.dy < 0 ? Wm : (o.dy > 0 ? Wp : Wc))[4 + p + R::delta(n)];
       });
       Draws<RNG_PHILOX> d;
       d.w1 = h ? blk.z : blk.x;
       d.w2 = h ? blk.w : blk.y;
-      int nw = site_event<MODEL, RNG_PHILOX, NN>(a.ev, cur[s], v, d);
-      // sites of the two outermost strips whose neighbours are already stale stay untouched
-      if (p < p_lo || p >= p_hi) nw = cur[s];
+      // (sites of the two outermost strips whose neighbours are already stale are updated too:
+      // they lie in the part of the halo that is stale from this step on and is never stored)
+      const int nw = site_event<MODEL, RNG_PHILOX, NN>(a.ev, cur[s], v, d);
       accepted += (nw != cur[s]);
       cur[s] = nw;
     });
   });
   // updated spins go back to the tile; they are never read again within this colour step
-  int32_t *own = tile + yl * T2_BW + e0;
   static_for<2>([&](auto C_) {
     constexpr int c = decltype(C_)::value;
     bool changed = false;
     static_for<NS>([&](auto S_) {
       constexpr int s = decltype(S_)::value, p = P + S * s;
-      if constexpr (p / 4 == c) { changed |= (cur[s] != before[s]); W[1][4 + p] = cur[s]; }
+      if constexpr (p / 4 == c) { changed |= (cur[s] != before[s]); Wc[4 + p] = cur[s]; }
     });
     if (changed)
-      *reinterpret_cast<int4 *>(own + 4 * c) = make_int4(W[1][4 + 4 * c], W[1][5 + 4 * c], W[1][6 + 4 * c], W[1][7 + 4 * c]);
+      *reinterpret_cast<int4 *>(own + 4 * c) = make_int4(Wc[4 + 4 * c], Wc[5 + 4 * c], Wc[6 + 4 * c], Wc[7 + 4 * c]);
   });
   return count ? accepted : 0;
 }
@@ -155,19 +154,22 @@ sweep_tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     __syncthreads();
 
     const int e0 = 8 * lane;  // this lane's strip inside the box
+    // global element of the strip start (strips are 8-aligned in the lattice and never straddle
+    // the row end) and whether the strip belongs to the stored interior
+    int xg = xb + e0;
+    xg %= rowlen;
+    if (xg < 0) xg += rowlen;
+    const bool x_interior = e0 >= C::HX && e0 < T2_BW - C::HX && xb + e0 < rowlen;
+    const unsigned long long rowsize = (unsigned long long)(g.gX * NB);
+
 #pragma unroll 1
     for (int c0 = 0; c0 < C::C; c0++) {
-      // rows that can be updated in step c0: all neighbours still valid
+      // rows that can be updated in step c0: all neighbours still valid (rect shrinks by one
+      // site reach per colour step); this warp's band of them
       const int ylo = c0 + 1, yhi = C::BH - c0 - 1;
-      const int xlo = C::RX * (c0 + 1), xhi = T2_BW - C::RX * (c0 + 1);
-      // this warp's band of rows
       const int nrow = yhi - ylo;
       const int y0 = ylo + (warp * nrow) / 8, y1 = ylo + ((warp + 1) * nrow) / 8;
-      // lanes 1..30 hold strips that are valid in every step (RX*C <= 8); lane 0 / 31 hold the halo
-      // strips, of which only the sites inside [xlo, xhi) may still be updated
-      const int p_lo = lane == 0 ? xlo : 0, p_hi = lane == 31 ? xhi - (T2_BW - 8) : 8;
       if (y0 < y1) {
-        int W[3][16];
         auto load_row = [&](int (&w)[16], int yl) {
           const int32_t *row = tile + yl * T2_BW + e0;
           load_chunk(w, 1, row, 0);
@@ -175,20 +177,12 @@ sweep_tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           if (e0 >= 4) load_chunk(w, 0, row, -4);
           if (e0 + 12 <= T2_BW) load_chunk(w, 3, row, 8);
         };
-        load_row(W[0], y0 - 1);
-        load_row(W[1], y0);
-        for (int yl = y0; yl < y1; yl++) {
-          load_row(W[2], yl + 1);
-          // global row of this tile row (ghost rows are periodic images)
-          int jg = g.g0 + yb + yl;
-          jg %= g.gY;
-          if (jg < 0) jg += g.gY;
-          int xg = xb + e0;  // global element of the strip start; strips never straddle the row end
-          xg %= rowlen;
-          if (xg < 0) xg += rowlen;
-          const unsigned long long grow = (unsigned long long)jg * (unsigned long long)(g.gX * NB) + xg;
-          const bool interior = yl >= C::HY && yl < C::HY + T2_OH && yb + yl < Y && e0 >= C::HX && e0 < T2_BW - C::HX &&
-                                xb + e0 < rowlen;
+        int jg = (g.g0 + yb + y0) % g.gY;  // global row of tile row y0 (ghost rows are periodic images)
+        if (jg < 0) jg += g.gY;
+        auto step = [&](int yl, const int (&Wm)[16], int (&Wc)[16], const int (&Wp)[16]) {
+          const unsigned long long grow = (unsigned long long)jg * rowsize + xg;
+          const bool interior = x_interior && yl >= C::HY && yl < C::HY + T2_OH && yb + yl < Y;
+          int32_t *own = tile + yl * T2_BW + e0;
           bool row_class = true;
           int P;
           if constexpr (LAT == SPK_SQ_4N) P = (c0 + jg) & 1;
@@ -197,18 +191,33 @@ sweep_tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           if (row_class) {
             if constexpr (LAT == SPK_TRI) {
               switch (P) {
-                case 0: accepted += tile2d_strip<LAT, MODEL, 0>(a, c0, tile, yl, e0, W, grow, interior, p_lo, p_hi); break;
-                case 1: accepted += tile2d_strip<LAT, MODEL, 1>(a, c0, tile, yl, e0, W, grow, interior, p_lo, p_hi); break;
-                case 2: accepted += tile2d_strip<LAT, MODEL, 2>(a, c0, tile, yl, e0, W, grow, interior, p_lo, p_hi); break;
-                default: accepted += tile2d_strip<LAT, MODEL, 3>(a, c0, tile, yl, e0, W, grow, interior, p_lo, p_hi); break;
+                case 0: accepted += tile2d_strip<LAT, MODEL, 0>(a, c0, own, Wm, Wc, Wp, grow, interior); break;
+                case 1: accepted += tile2d_strip<LAT, MODEL, 1>(a, c0, own, Wm, Wc, Wp, grow, interior); break;
+                case 2: accepted += tile2d_strip<LAT, MODEL, 2>(a, c0, own, Wm, Wc, Wp, grow, interior); break;
+                default: accepted += tile2d_strip<LAT, MODEL, 3>(a, c0, own, Wm, Wc, Wp, grow, interior); break;
               }
             } else {
-              if (P) accepted += tile2d_strip<LAT, MODEL, 1>(a, c0, tile, yl, e0, W, grow, interior, p_lo, p_hi);
-              else accepted += tile2d_strip<LAT, MODEL, 0>(a, c0, tile, yl, e0, W, grow, interior, p_lo, p_hi);
+              if (P) accepted += tile2d_strip<LAT, MODEL, 1>(a, c0, own, Wm, Wc, Wp, grow, interior);
+              else accepted += tile2d_strip<LAT, MODEL, 0>(a, c0, own, Wm, Wc, Wp, grow, interior);
             }
           }
-#pragma unroll
-          for (int i = 0; i < 16; i++) { W[0][i] = W[1][i]; W[1][i] = W[2][i]; }
+          if (++jg == g.gY) jg = 0;
+        };
+        // three register windows take turns as the rows above / at / below (no register copies)
+        int A[16], B[16], Cw[16];
+        load_row(A, y0 - 1);
+        load_row(B, y0);
+        for (int yl = y0; yl < y1; yl += 3) {
+          load_row(Cw, yl + 1);
+          step(yl, A, B, Cw);
+          if (yl + 1 < y1) {
+            load_row(A, yl + 2);
+            step(yl + 1, B, Cw, A);
+          }
+          if (yl + 2 < y1) {
+            load_row(B, yl + 3);
+            step(yl + 2, Cw, A, B);
+          }
         }
       }
       __syncthreads();
