@@ -62,12 +62,19 @@ template <> struct Draws<RNG_STRICT> { int seed; };
 // passed through kernel parameters so that ptxas keeps the multiply-add form and the two integer
 // pipes stay balanced; nvcc's own code for `e += (v != s)` costs 2.4-3.2 ALU-heavy instructions.
 template <int NN> __device__ __forceinline__ int unlike(const int (&v)[NN], int value, int one) {
-  int e[4] = {0, 0, 0, 0};
+  // two accumulator chains (the sites of a strip interleave, so four chains are in flight); the
+  // first compare of each chain writes its result directly instead of adding to a zeroed register
+  int e[2];
 #pragma unroll
-  for (int n = 0; n < NN; n++)
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, %2;\n\t@p mad.lo.s32 %0, %3, %3, %0;\n\t}"
-        : "+r"(e[n & 3]) : "r"(v[n]), "r"(value), "r"(one));
-  return (e[0] + e[1]) + (e[2] + e[3]);
+  for (int n = 0; n < NN; n++) {
+    if (n < 2)
+      asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, %2;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+          : "=r"(e[n]) : "r"(v[n]), "r"(value));
+    else
+      asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, %2;\n\t@p mad.lo.s32 %0, %3, %3, %0;\n\t}"
+          : "+r"(e[n & 1]) : "r"(v[n]), "r"(value), "r"(one));
+  }
+  return NN > 1 ? e[0] + e[1] : e[0];
 }
 
 // position of the pick-th (0-based) set bit of m; pick < popc(m)
@@ -145,13 +152,16 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
   if constexpr (MODEL == SPK_ISING) {
     // two-state shortcut: with spins in {1,2} the neighbours unlike `old` are exactly the ones
     // like a different trial, so efinal = NN - einitial and no second count is needed
-    if (trial == old) return old;
     const int dE2 = NN - 2 * e0;
-    if (dE2 <= 0) return trial;
-    if (p.t_zero) return old;
     if constexpr (RNG == RNG_PHILOX) {
-      return d.w2 > p.thr[dE2] ? old : trial;
+      // branch-free: thr[0] = 2^32-1 accepts every dE <= 0; T = 0 has thr[dE>0] = 0 and must
+      // not accept on w2 == 0, hence the explicit t_zero term
+      const bool ok = (dE2 <= 0) || (!p.t_zero && d.w2 <= p.thr[dE2 > 0 ? dE2 : 0]);
+      return ok ? trial : old;
     } else {
+      if (trial == old) return old;
+      if (dE2 <= 0) return trial;
+      if (p.t_zero) return old;
       double u;
       if constexpr (RNG == RNG_INJECTED) u = d.u2;
       else u = park_uniform(d.seed);
