@@ -29,6 +29,22 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
+// Same function with the ten round keys precomputed on the host (EventParams::rk): the key
+// schedule then costs no instructions, the keys are constant-bank operands of the XORs.
+struct PhiloxKeys { uint32_t k[20]; };
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &rk) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ rk.k[2 * r];
+    c2 = hi0 ^ c3 ^ rk.k[2 * r + 1];
+    c1 = lo1;
+    c3 = lo0;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
 // RandomPark::uniform (src/random_park.cpp:79-86) as 16807*seed mod (2^31-1); the Schrage form
 // of the reference and this 64-bit product give the same residue for seed in [1, 2^31-2].
 __device__ __forceinline__ double park_uniform(int &seed) {
@@ -45,6 +61,7 @@ struct EventParams {
   int t_zero;               // temperature == 0.0
   int one;                  // the constant 1, opaque to the compiler (see unlike())
   uint32_t k0, k1;          // Philox key (seed)
+  PhiloxKeys rk;            // its ten round keys (host-side key schedule)
   uint32_t sweep;           // Philox counter word 2
   uint32_t thr[27];         // Philox mode: floor(exp(-dE/T) * 2^32), dE = 1..26 (host libm)
   double ptab[27];          // double modes: exp((double)(-dE) * t_inverse)       (host libm)

@@ -117,6 +117,10 @@ void build_tables(spk_cuda_handle *h) {
   ev.one = 1;
   ev.k0 = (uint32_t)h->d.seed;
   ev.k1 = (uint32_t)(h->d.seed >> 32);
+  for (int r = 0; r < 10; r++) {  // Philox key schedule: key + r * Weyl constants
+    ev.rk.k[2 * r] = ev.k0 + (uint32_t)r * 0x9E3779B9u;
+    ev.rk.k[2 * r + 1] = ev.k1 + (uint32_t)r * 0xBB67AE85u;
+  }
   ev.sweep = 0;
   const double t_inverse = ev.t_zero ? 0.0 : 1.0 / h->d.temperature;
   for (int dE = 0; dE < 27; dE++) {
@@ -352,12 +356,17 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-      if (cudaFuncSetAttribute(sweep_stream_kernel<LAT, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      if (cudaFuncSetAttribute(sweep_stream_kernel<LAT, MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               C::SMEM_BYTES) != cudaSuccess ||
+          cudaFuncSetAttribute(sweep_stream_kernel<LAT, MODEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                C::SMEM_BYTES) != cudaSuccess)
         return 1;
       attr_set = true;
     }
-    sweep_stream_kernel<LAT, MODEL><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, args, sm);
+    if (args.nloop == 1)
+      sweep_stream_kernel<LAT, MODEL, true><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, args, sm);
+    else
+      sweep_stream_kernel<LAT, MODEL, false><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, args, sm);
     h->launches++;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
   }

@@ -122,7 +122,7 @@ __device__ __forceinline__ void patch_store(const PatchPlan &pp, int32_t *pl, in
 }
 
 // one class row of one class plane: the thread's 16-byte chunk holds two class sites at P, P+2
-template <int LAT, int MODEL, int P>
+template <int LAT, int MODEL, int P, bool ONEPASS>
 __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *const (&pl)[3], int r, int lane,
                                             int32_t *gchunk, unsigned long long gsite0) {
   using L = Lat<LAT>;
@@ -145,9 +145,11 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
   const int before0 = cur[0], before1 = cur[1];
   int accepted = 0;
   const unsigned long long leader = gsite0 + P;
-  for (int l = 0; l < a.nloop; l++) {
+  const int nloop = ONEPASS ? 1 : a.nloop;  // ONEPASS: the common nloop == 1 without loop overhead
+#pragma unroll
+  for (int l = 0; l < nloop; l++) {
     const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep,
-                                    (uint32_t)l * 16u + (uint32_t)(a.c0 + 1), a.ev.k0, a.ev.k1);
+                                    (uint32_t)l * 16u + (uint32_t)(a.c0 + 1), a.ev.rk);
     static_for<2>([&](auto H) {
       constexpr int h = decltype(H)::value, e = P + 2 * h;
       int v[NN];
@@ -172,7 +174,7 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
   return accepted;
 }
 
-template <int LAT, int MODEL>
+template <int LAT, int MODEL, bool ONEPASS>
 __global__ void __launch_bounds__(256, 2)
 sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SweepArgs a,
                     const __grid_constant__ StreamMap sm) {
@@ -266,8 +268,8 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           int32_t *gchunk = a.spin + (long long)k * sz + (long long)y * sy + x;
           const unsigned long long gsite0 =
               ((unsigned long long)(k + g.g0) * g.gY + y) * (unsigned long long)g.gX + x;
-          if (px) accepted += stream_chunk<LAT, MODEL, 1>(a, pl, r, lane, gchunk, gsite0);
-          else accepted += stream_chunk<LAT, MODEL, 0>(a, pl, r, lane, gchunk, gsite0);
+          if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS>(a, pl, r, lane, gchunk, gsite0);
+          else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS>(a, pl, r, lane, gchunk, gsite0);
         }
       }
       __syncthreads();  // planes k-1 (and k) may now be overwritten by the next step's loads

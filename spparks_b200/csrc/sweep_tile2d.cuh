@@ -71,7 +71,7 @@ __device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t 
     constexpr int pr = decltype(PR)::value;
     const unsigned long long leader = grow + P + S * (2 * pr);
     const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep, (uint32_t)(c0 + 1),
-                                    a.ev.k0, a.ev.k1);
+                                    a.ev.rk);
     static_for<2>([&](auto H) {
       constexpr int h = decltype(H)::value, s = 2 * pr + h, p = P + S * s;
       int v[NN];

@@ -117,7 +117,7 @@ __device__ __forceinline__ int strip_body(const SweepArgs &a, int e0, int j, int
       constexpr int pr = decltype(PR)::value;
       const unsigned long long leader = grow + P + S * (2 * pr);
       const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep,
-                                      (uint32_t)l * 16u + (uint32_t)(a.c0 + 1), a.ev.k0, a.ev.k1);
+                                      (uint32_t)l * 16u + (uint32_t)(a.c0 + 1), a.ev.rk);
       static_for<2>([&](auto H) {
         constexpr int h = decltype(H)::value, s = 2 * pr + h, p = P + S * s;
         int v[NN];
