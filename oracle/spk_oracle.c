@@ -342,7 +342,7 @@ int64_t orc_halfsweep_injected(const orc_ctx *c, int32_t *spin, int color, const
  * cell index i differs only in bit 1 (i and i^2, same j,k,basis): counter = (leader lo, leader hi,
  * sweep, iloop*16+color) with leader = index of the site with bit 1 of i cleared, key = seed.
  * The site with bit 1 clear consumes words (0,1), the other one words (2,3); the first word plays
- * u1 = w/2^32 and the second u2.  With those exactly representable uniforms the reference's
+ * u1 = w/2^32 and the second u2.  (ising: four sites per block, see philox_event.)  With those exactly representable uniforms the reference's
  * double formulas reduce to the integer forms below, which is what the CUDA kernels evaluate:
  *   ising:      u1 < 0.5            <=>  w < 2^31
  *   potts/pin:  (int)(Q*u1)+1        =   ((Q*w) >> 32) + 1          (Q < 2^31)
@@ -362,12 +362,24 @@ static int philox_event(const orc_ctx *c, int32_t *spin, int64_t site, uint64_t 
   if (c->cfg.model == ORC_POTTS_PIN && old > Q) return 0;
   int ci, cj, ck, cm;
   site_ijkm(c, site, &ci, &cj, &ck, &cm);
-  const int second = (ci >> 1) & 1;
-  const uint64_t leader = (uint64_t)site - (second ? 2u * (uint64_t)c->nbasis : 0u);
-  uint32_t ctr[4] = {(uint32_t)leader, (uint32_t)(leader >> 32), sweep, (uint32_t)iloop * 16u + (uint32_t)color};
+  uint64_t leader;
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, blk[4], w[2];
+  if (c->cfg.model == ORC_ISING) {
+    /* ising needs one bit for the trial spin: one block serves the FOUR same-colour sites whose
+     * cell index differs only in bits 1,2; site number (i>>1)&3 takes word w of the block:
+     * u1 = top bit of w (trial = 1 + bit), u2 = (w mod 2^31)/2^31, i.e. second word = w << 1 */
+    leader = (uint64_t)site - (uint64_t)(ci & 6) * (uint64_t)c->nbasis;
+  } else {
+    leader = (uint64_t)site - (((ci >> 1) & 1) ? 2u * (uint64_t)c->nbasis : 0u);
+  }
+  uint32_t ctr[4] = {(uint32_t)leader, (uint32_t)(leader >> 32), sweep, (uint32_t)iloop * 16u + (uint32_t)color};
   orc_philox4x32_10(ctr, key, blk);
-  w[0] = blk[2 * second]; w[1] = blk[2 * second + 1];
+  if (c->cfg.model == ORC_ISING) {
+    w[0] = blk[(ci >> 1) & 3]; w[1] = w[0] << 1;
+  } else {
+    const int second = (ci >> 1) & 1;
+    w[0] = blk[2 * second]; w[1] = blk[2 * second + 1];
+  }
 
   int64_t nb[ORC_MAXNEIGH];
   orc_neighbors(c, site, nb);

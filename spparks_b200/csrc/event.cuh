@@ -45,6 +45,27 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
+// Which Philox block and which words serve the class site at cell index i (global).
+//   potts family: two sites per block (cells i, i^2): leader has bit 1 of i cleared, the site
+//                 with bit 1 clear takes (x,y), the other (z,w)
+//   ising:        four sites per block (cells differing in bits 1,2): the trial spin needs one
+//                 bit only, so site (i>>1)&3 takes ONE word w: u1 = its top bit, u2 = (w mod 2^31)/2^31,
+//                 expressed as second word = w << 1 so that `w2 > thr` is unchanged
+template <int MODEL> __device__ __forceinline__ int philox_leader_shift(int i) {
+  return MODEL == SPK_ISING ? (i & 6) : (i & 2);  // cells between the site and its block leader
+}
+template <int MODEL> __device__ __forceinline__ void philox_words(const uint4 &blk, int i, uint32_t &w1, uint32_t &w2) {
+  if (MODEL == SPK_ISING) {
+    const int s = (i >> 1) & 3;
+    w1 = s == 0 ? blk.x : (s == 1 ? blk.y : (s == 2 ? blk.z : blk.w));
+    w2 = w1 << 1;
+  } else {
+    const bool second = (i >> 1) & 1;
+    w1 = second ? blk.z : blk.x;
+    w2 = second ? blk.w : blk.y;
+  }
+}
+
 // RandomPark::uniform (src/random_park.cpp:79-86) as 16807*seed mod (2^31-1); the Schrage form
 // of the reference and this 64-bit product give the same residue for seed in [1, 2^31-2].
 __device__ __forceinline__ double park_uniform(int &seed) {

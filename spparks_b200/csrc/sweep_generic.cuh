@@ -121,14 +121,13 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const __grid_constan
       accepted += (nw != cur);
       cur = nw;
     } else {
-      const bool second = (i >> 1) & 1;  // partner of the site at i^2 in the shared Philox block
-      const unsigned long long leader = gsite - (second ? 2ull * NB : 0ull);
+      // block shared with the other class sites of the strip (event.cuh: philox_words)
+      const unsigned long long leader = gsite - (unsigned long long)(philox_leader_shift<MODEL>(i) * NB);
       for (int l = 0; l < a.nloop; l++) {
         const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep,
                                         (uint32_t)l * 16u + (uint32_t)(a.c0 + 1), a.ev.k0, a.ev.k1);
         Draws<RNG_PHILOX> d;
-        d.w1 = second ? blk.z : blk.x;
-        d.w2 = second ? blk.w : blk.y;
+        philox_words<MODEL>(blk, i, d.w1, d.w2);
         int nw = site_event<MODEL, RNG, NN>(a.ev, cur, v, d);
         accepted += (nw != cur);
         cur = nw;

@@ -124,7 +124,7 @@ __device__ __forceinline__ void patch_store(const PatchPlan &pp, int32_t *pl, in
 // one class row of one class plane: the thread's 16-byte chunk holds two class sites at P, P+2
 template <int LAT, int MODEL, int P, bool ONEPASS>
 __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *const (&pl)[3], int r, int lane,
-                                            int32_t *gchunk, unsigned long long gsite0) {
+                                            int32_t *gchunk, unsigned long long gsite0, int xcell) {
   using L = Lat<LAT>;
   constexpr int NN = L::NN;
   using R = RowInfo<LAT, 0>;
@@ -144,7 +144,10 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
   int cur[2] = {W[4][1 + P], W[4][3 + P]};
   const int before0 = cur[0], before1 = cur[1];
   int accepted = 0;
-  const unsigned long long leader = gsite0 + P;
+  // Philox block of the chunk's two class sites (event.cuh: philox_words); an ising block spans
+  // two chunks, this one is its upper half when bit 2 of the (4-aligned) chunk start is set
+  const bool upper = MODEL == SPK_ISING ? ((xcell >> 2) & 1) : false;
+  const unsigned long long leader = gsite0 + P - (upper ? 4 : 0);
   const int nloop = ONEPASS ? 1 : a.nloop;  // ONEPASS: the common nloop == 1 without loop overhead
 #pragma unroll
   for (int l = 0; l < nloop; l++) {
@@ -159,8 +162,13 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
         v[n] = W[(o.dz + 1) * 3 + (o.dy + 1)][1 + e + o.dx];
       });
       Draws<RNG_PHILOX> d;
-      d.w1 = h ? blk.z : blk.x;
-      d.w2 = h ? blk.w : blk.y;
+      if constexpr (MODEL == SPK_ISING) {
+        d.w1 = upper ? (h ? blk.w : blk.z) : (h ? blk.y : blk.x);
+        d.w2 = d.w1 << 1;
+      } else {
+        d.w1 = h ? blk.z : blk.x;
+        d.w2 = h ? blk.w : blk.y;
+      }
       const int nw = site_event<MODEL, RNG_PHILOX, NN>(a.ev, cur[h], v, d);
       accepted += (nw != cur[h]);
       cur[h] = nw;
@@ -268,8 +276,8 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           int32_t *gchunk = a.spin + (long long)k * sz + (long long)y * sy + x;
           const unsigned long long gsite0 =
               ((unsigned long long)(k + g.g0) * g.gY + y) * (unsigned long long)g.gX + x;
-          if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS>(a, pl, r, lane, gchunk, gsite0);
-          else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS>(a, pl, r, lane, gchunk, gsite0);
+          if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS>(a, pl, r, lane, gchunk, gsite0, x);
+          else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS>(a, pl, r, lane, gchunk, gsite0, x);
         }
       }
       __syncthreads();  // planes k-1 (and k) may now be overwritten by the next step's loads

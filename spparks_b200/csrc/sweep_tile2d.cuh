@@ -55,7 +55,7 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 // one 8-element strip of one row for colour step c0; P = offset of the first class site
 template <int LAT, int MODEL, int P>
 __device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t *own, const int (&Wm)[16], int (&Wc)[16],
-                                            const int (&Wp)[16], unsigned long long grow, bool count) {
+                                            const int (&Wp)[16], unsigned long long grow, int xg, bool count) {
   using L = Lat<LAT>;
   constexpr int NN = L::NN, NB = L::NB;
   constexpr int S = 2 * NB, NS = 8 / S;
@@ -67,13 +67,16 @@ __device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t 
     before[s] = cur[s] = Wc[4 + P + S * s];
   });
   int accepted = 0;
-  static_for<NS / 2>([&](auto PR) {
+  constexpr int SPB = (MODEL == SPK_ISING) ? 4 : 2;  // class sites per Philox block (event.cuh)
+  constexpr int NBLK = (NS + SPB - 1) / SPB;
+  static_for<NBLK>([&](auto PR) {
     constexpr int pr = decltype(PR)::value;
-    const unsigned long long leader = grow + P + S * (2 * pr);
+    const bool upper = (MODEL == SPK_ISING && NS < SPB) ? ((xg >> 3) & 1) : false;
+    const unsigned long long leader = grow + P + S * (SPB * pr) - (upper ? 8 : 0);
     const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep, (uint32_t)(c0 + 1),
                                     a.ev.rk);
-    static_for<2>([&](auto H) {
-      constexpr int h = decltype(H)::value, s = 2 * pr + h, p = P + S * s;
+    static_for<(NS < SPB ? NS : SPB)>([&](auto H) {
+      constexpr int h = decltype(H)::value, s = SPB * pr + h, p = P + S * s;
       int v[NN];
       static_for<NN>([&](auto N_) {
         constexpr int n = decltype(N_)::value;
@@ -81,8 +84,15 @@ __device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t 
         v[n] = (o.dy < 0 ? Wm : (o.dy > 0 ? Wp : Wc))[4 + p + R::delta(n)];
       });
       Draws<RNG_PHILOX> d;
-      d.w1 = h ? blk.z : blk.x;
-      d.w2 = h ? blk.w : blk.y;
+      if constexpr (MODEL == SPK_ISING) {
+        const uint32_t lo = h == 0 ? blk.x : (h == 1 ? blk.y : (h == 2 ? blk.z : blk.w));
+        const uint32_t hi = h == 0 ? blk.z : blk.w;
+        d.w1 = upper ? hi : lo;
+        d.w2 = d.w1 << 1;
+      } else {
+        d.w1 = h ? blk.z : blk.x;
+        d.w2 = h ? blk.w : blk.y;
+      }
       // (sites of the two outermost strips whose neighbours are already stale are updated too:
       // they lie in the part of the halo that is stale from this step on and is never stored)
       const int nw = site_event<MODEL, RNG_PHILOX, NN>(a.ev, cur[s], v, d);
@@ -191,14 +201,14 @@ sweep_tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           if (row_class) {
             if constexpr (LAT == SPK_TRI) {
               switch (P) {
-                case 0: accepted += tile2d_strip<LAT, MODEL, 0>(a, c0, own, Wm, Wc, Wp, grow, interior); break;
-                case 1: accepted += tile2d_strip<LAT, MODEL, 1>(a, c0, own, Wm, Wc, Wp, grow, interior); break;
-                case 2: accepted += tile2d_strip<LAT, MODEL, 2>(a, c0, own, Wm, Wc, Wp, grow, interior); break;
-                default: accepted += tile2d_strip<LAT, MODEL, 3>(a, c0, own, Wm, Wc, Wp, grow, interior); break;
+                case 0: accepted += tile2d_strip<LAT, MODEL, 0>(a, c0, own, Wm, Wc, Wp, grow, xg, interior); break;
+                case 1: accepted += tile2d_strip<LAT, MODEL, 1>(a, c0, own, Wm, Wc, Wp, grow, xg, interior); break;
+                case 2: accepted += tile2d_strip<LAT, MODEL, 2>(a, c0, own, Wm, Wc, Wp, grow, xg, interior); break;
+                default: accepted += tile2d_strip<LAT, MODEL, 3>(a, c0, own, Wm, Wc, Wp, grow, xg, interior); break;
               }
             } else {
-              if (P) accepted += tile2d_strip<LAT, MODEL, 1>(a, c0, own, Wm, Wc, Wp, grow, interior);
-              else accepted += tile2d_strip<LAT, MODEL, 0>(a, c0, own, Wm, Wc, Wp, grow, interior);
+              if (P) accepted += tile2d_strip<LAT, MODEL, 1>(a, c0, own, Wm, Wc, Wp, grow, xg, interior);
+              else accepted += tile2d_strip<LAT, MODEL, 0>(a, c0, own, Wm, Wc, Wp, grow, xg, interior);
             }
           }
           if (++jg == g.gY) jg = 0;

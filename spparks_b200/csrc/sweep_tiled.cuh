@@ -113,13 +113,19 @@ __device__ __forceinline__ int strip_body(const SweepArgs &a, int e0, int j, int
 
   int accepted = 0;
   for (int l = 0; l < a.nloop; l++) {
-    static_for<NS / 2>([&](auto PR) {
+    // Philox blocks of the strip (event.cuh: philox_words): potts family one block per pair of
+    // class sites, ising one block per four
+    constexpr int SPB = (MODEL == SPK_ISING) ? 4 : 2;           // class sites per block
+    constexpr int NBLK = (NS + SPB - 1) / SPB;                  // blocks the strip touches
+    static_for<NBLK>([&](auto PR) {
       constexpr int pr = decltype(PR)::value;
-      const unsigned long long leader = grow + P + S * (2 * pr);
+      // strips are 8-element aligned; a tri strip (4 cells) is half of an ising block
+      const bool upper = (MODEL == SPK_ISING && NS < SPB) ? ((e0 >> 3) & 1) : false;
+      const unsigned long long leader = grow + P + S * (SPB * pr) - (upper ? 8 : 0);
       const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep,
                                       (uint32_t)l * 16u + (uint32_t)(a.c0 + 1), a.ev.rk);
-      static_for<2>([&](auto H) {
-        constexpr int h = decltype(H)::value, s = 2 * pr + h, p = P + S * s;
+      static_for<(NS < SPB ? NS : SPB)>([&](auto H) {
+        constexpr int h = decltype(H)::value, s = SPB * pr + h, p = P + S * s;
         int v[NN];
         static_for<NN>([&](auto N_) {
           constexpr int n = decltype(N_)::value;
@@ -128,8 +134,15 @@ __device__ __forceinline__ int strip_body(const SweepArgs &a, int e0, int j, int
           v[n] = W[row][idx];
         });
         Draws<RNG_PHILOX> d;
-        d.w1 = h ? blk.z : blk.x;
-        d.w2 = h ? blk.w : blk.y;
+        if constexpr (MODEL == SPK_ISING) {
+          const uint32_t lo = h == 0 ? blk.x : (h == 1 ? blk.y : (h == 2 ? blk.z : blk.w));
+          const uint32_t hi = h == 0 ? blk.z : blk.w;  // (only h < 2 when the strip is the upper half)
+          d.w1 = upper ? hi : lo;
+          d.w2 = d.w1 << 1;
+        } else {
+          d.w1 = h ? blk.z : blk.x;
+          d.w2 = h ? blk.w : blk.y;
+        }
         const int nw = site_event<MODEL, RNG_PHILOX, NN>(a.ev, cur[s], v, d);
         accepted += (nw != cur[s]);
         cur[s] = nw;
