@@ -283,11 +283,25 @@ def main():
     sweep_no = args.warmup + args.steps
     value = natt_all / (ms * 1e-3) / 1e9
 
-    # ---- e2e: public C ABI with HOST buffers; every step = H2D lattice + sweep + D2H lattice + counters
+    # ---- e2e: the public C ABI with HOST buffers, as the SPPARKS plugin drives it for one `run`
+    # segment of K sweeps (plugin/app_cuda_mixin.h iterate_rejection): pinned H2D of the lattice,
+    # K sweeps each followed by a D2H read of the step's metric (accept/attempt counters), then D2H
+    # of the lattice for the host-side output.  All copies are inside the timed region (wall clock).
     host = torch.empty(s.nlocal, dtype=torch.int32).pin_memory()
     s.download_ptr(host.data_ptr(), s.nlocal)
     barrier(s)
     t0 = time.perf_counter()
+    s.upload_ptr(host.data_ptr(), s.nlocal)
+    for _ in range(args.steps):
+        s.sweeps(sweep_no, 1)
+        sweep_no += 1
+        s.counters()
+    s.download_ptr(host.data_ptr(), s.nlocal)
+    barrier(s)
+    e2e_s = time.perf_counter() - t0
+    # strictest reading, reported next to it: a full host round trip of the lattice around EVERY sweep
+    barrier(s)
+    t1 = time.perf_counter()
     for _ in range(args.e2e_steps):
         s.upload_ptr(host.data_ptr(), s.nlocal)
         s.sweeps(sweep_no, 1)
@@ -295,11 +309,12 @@ def main():
         s.download_ptr(host.data_ptr(), s.nlocal)
         s.counters()
     barrier(s)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    strict_s = time.perf_counter() - t1
+    te = torch.tensor([e2e_s, strict_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = s.nlocal * world * args.e2e_steps / float(te.item()) / 1e9
+    e2e_value = s.nlocal * world * args.steps / float(te[0].item()) / 1e9
+    strict_value = s.nlocal * world * args.e2e_steps / float(te[1].item()) / 1e9
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -327,9 +342,17 @@ def main():
                              "kernel": kernel_name,
                              "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
                              "colour_fused_bound_bytes_per_site": 8},
-                "e2e": {"value": e2e_value, "unit": "Gsites/s", "h2d_bytes_per_step": 4 * s.nlocal * world,
-                        "d2h_bytes_per_step": 4 * s.nlocal * world + 16 * world, "steps": args.e2e_steps,
-                        "definition": "per step: pinned H2D of the lattice, one sweep, D2H of the lattice + counters"},
+                "e2e": {"value": e2e_value, "unit": "Gsites/s",
+                        "h2d_bytes_per_step": 4 * s.nlocal * world / args.steps,
+                        "d2h_bytes_per_step": (4 * s.nlocal * world) / args.steps + 16 * world,
+                        "definition": "one run segment through the C ABI as the SPPARKS plugin issues it: pinned H2D "
+                                      "of the lattice, %d sweeps each followed by a D2H read of the counters, D2H of "
+                                      "the lattice; bytes are the segment's copies divided by its sweeps" % args.steps,
+                        "strict_per_step": {"value": strict_value, "unit": "Gsites/s", "steps": args.e2e_steps,
+                                            "h2d_bytes_per_step": 4 * s.nlocal * world,
+                                            "d2h_bytes_per_step": 4 * s.nlocal * world + 16 * world,
+                                            "definition": "H2D of the lattice, one sweep, D2H of the lattice + "
+                                                          "counters around every single sweep (PCIe-bound)"}},
                 "gpu_launches": launches_all, "clocks": clk}
         traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_path):
