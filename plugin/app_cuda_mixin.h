@@ -167,10 +167,20 @@ class AppCudaMixin : public Base {
     // one set per sector and nloop/nselect chosen so that every site is attempted nstop times
 
     int nsector = this->nsector;
+
+    // whole-lattice colour sweeps with one pass per set (the common case: `sweep color`,
+    // `sector no`) go through spk_cuda_sweeps, which is bit-identical to the per-colour calls
+    // below but may fuse the colours of a sweep into one launch
+
+    int whole = (!strict && nsector == 1);
+    for (int icolor = 0; whole && icolor < ncolor; icolor++)
+      if (set_nloop(0,icolor,ncolor) != 1) whole = 0;
+
     int done = 0;
     while (!done) {
       this->timer->stamp();
-      for (int isector = 0; isector < nsector; isector++) {
+      if (whole) check(spk_cuda_sweeps(handle,sweep_counter,1));
+      else for (int isector = 0; isector < nsector; isector++) {
         int box[6];
         sector_box(isector,nsector,box);
         for (int icolor = 0; icolor < ncolor; icolor++) {

@@ -114,3 +114,51 @@ run 100.0
     assert [r[3] for r in rows] == [str(20 * i) for i in range(11)]
     assert int(rows[-1][1]) + int(rows[-1][2]) == 500000
     assert 150 <= float(rows[-1][4]) <= 700
+
+
+@pytest.mark.parametrize("app,q,dim,lat,n,T", [
+    ("ising", 2, 2, "sq/4n", (64, 32, 1), 1.2),
+    ("potts", 30, 2, "tri", (32, 20, 1), 0.5),
+    ("potts/neighonly", 40, 3, "sc/26n", (16, 16, 12), 0.5),
+], ids=["ising-sq4n", "potts-tri", "neighonly-sc26n"])
+def test_color_sweep_script_matches_library_and_oracle(app, q, dim, lat, n, T):
+    """`sweep color` through the plugin (Philox stream, `cuda_seed` fixed) prints the Naccept and
+    Energy that the C ABI driven from Python and the CPU oracle produce for the same seed and the same
+    `set site range` lattice (whose reference stream the oracle restates)."""
+    import numpy as np
+    import oracle_py as O
+    from spparks_b200 import LatticeSweep
+    style = app + "/cuda" if app == "ising" else "%s/cuda %d" % (app, q)
+    dt = 0.5 if app == "ising" else (1.0 / 26 if app == "potts/neighonly" else 1.0 / q)
+    zr = "0 %d" % n[2] if dim == 3 else "-0.5 0.5"
+    script = """seed 4242
+app_style %s
+dimension %d
+lattice %s 1.0
+region box block 0 %d 0 %d %s
+create_box box
+create_sites box
+set site range 1 %d
+cuda_seed 987654321
+sweep color
+sector no
+temperature %r
+diag_style energy
+stats %.17g
+run %.17g
+""" % (style, dim, lat, n[0], n[1], zr, q, T, dt * 0.999, dt * 5.5)
+    rows = stats_rows(run(SPK_CUDA, script))
+    assert [r[3] for r in rows] == [str(i) for i in range(7)]
+    o = O.Oracle(app, lat, n[0], n[1], n[2], q, T)
+    m = O.mars(4242)
+    spins = o.set_site_range(1, q, m)
+    s = LatticeSweep(app, lat, n[0], n[1], n[2], nspins=q, temperature=T, seed=987654321)
+    s.upload(spins)
+    want = spins.copy()
+    nacc = 0
+    assert float(rows[0][4]) == o.total_energy(want)
+    for sw in range(6):
+        s.sweeps(sw, 1)
+        nacc += o.sweep_philox(want, 987654321, sw)
+        assert int(rows[sw + 1][1]) == s.counters()[0] == nacc
+        assert float(rows[sw + 1][4]) == s.energy() == o.total_energy(want)
