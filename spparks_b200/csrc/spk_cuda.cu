@@ -255,8 +255,10 @@ int refresh_ghosts_local(spk_cuda_handle *h) {
 }
 
 // whole colour-fused sweep of a 2-D lattice; returns 0 launched, -1 not applicable, >0 error
+// part: 0 = every tile row and swap the buffers; 1 = first and last tile row only (the rows the
+// neighbours' ghost rows depend on); 2 = the tile rows in between, then swap the buffers
 template <int LAT, int MODEL>
-int launch_tile2d(spk_cuda_handle *h, const SweepArgs &a) {
+int launch_tile2d(spk_cuda_handle *h, const SweepArgs &a, int part) {
   if constexpr (Lat<LAT>::DIM != 2) {
     return -1;
   } else {
@@ -266,8 +268,20 @@ int launch_tile2d(spk_cuda_handle *h, const SweepArgs &a) {
     Tile2dMap tm;
     tm.ntx = (rowlen + C::OW - 1) / C::OW;
     tm.nty = (h->nslab + T2_OH - 1) / T2_OH;
-    tm.items = tm.ntx * tm.nty;
     tm.gh = h->gh;
+    tm.ty0 = 0; tm.ty_run = tm.nty; tm.ty_alt = -1;
+    if (part == 1) { tm.ty_run = tm.nty > 1 ? 2 : 1; tm.ty_alt = tm.nty > 1 ? tm.nty - 1 : -1; }
+    if (part == 2) { tm.ty0 = 1; tm.ty_run = tm.nty - 2; }
+    tm.items = tm.ntx * tm.ty_run;
+    const bool swap_after = part != 1;
+    if (tm.ty_run <= 0) {
+      if (swap_after) {
+        std::swap(h->base, h->base_alt);
+        std::swap(h->tmap, h->tmap_alt);
+        h->spin = h->base + (int64_t)h->gh * h->plane;
+      }
+      return 0;
+    }
     static bool attr_set = false;
     if (!attr_set) {
       if (cudaFuncSetAttribute(sweep_tile2d_kernel<LAT, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -281,26 +295,28 @@ int launch_tile2d(spk_cuda_handle *h, const SweepArgs &a) {
     sweep_tile2d_kernel<LAT, MODEL><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, a, tm, dst);
     h->launches++;
     if (cudaGetLastError() != cudaSuccess) return 1;
-    // the destination becomes the lattice (stream order makes this safe for later launches)
-    std::swap(h->base, h->base_alt);
-    std::swap(h->tmap, h->tmap_alt);
-    h->spin = h->base + (int64_t)h->gh * h->plane;
+    if (swap_after) {  // the destination becomes the lattice (stream order makes this safe for later launches)
+      std::swap(h->base, h->base_alt);
+      std::swap(h->tmap, h->tmap_alt);
+      h->spin = h->base + (int64_t)h->gh * h->plane;
+    }
     return 0;
   }
 }
 
-template <int LAT> int fused_sweep_l(spk_cuda_handle *h, const SweepArgs &a) {
+template <int LAT> int fused_sweep_l(spk_cuda_handle *h, const SweepArgs &a, int part) {
   switch (h->d.model) {
-    case SPK_ISING: return launch_tile2d<LAT, SPK_ISING>(h, a);
-    case SPK_POTTS: return launch_tile2d<LAT, SPK_POTTS>(h, a);
-    case SPK_POTTS_NEIGHONLY: return launch_tile2d<LAT, SPK_POTTS_NEIGHONLY>(h, a);
-    case SPK_POTTS_PIN: return launch_tile2d<LAT, SPK_POTTS_PIN>(h, a);
+    case SPK_ISING: return launch_tile2d<LAT, SPK_ISING>(h, a, part);
+    case SPK_POTTS: return launch_tile2d<LAT, SPK_POTTS>(h, a, part);
+    case SPK_POTTS_NEIGHONLY: return launch_tile2d<LAT, SPK_POTTS_NEIGHONLY>(h, a, part);
+    case SPK_POTTS_PIN: return launch_tile2d<LAT, SPK_POTTS_PIN>(h, a, part);
   }
   return -1;
 }
 
-// one whole sweep (all colours) in one launch where a fused kernel exists: 0 done, -1 not applicable
-int fused_sweep(spk_cuda_handle *h) {
+// one whole sweep (all colours) by the fused 2-D kernel (part: see launch_tile2d): 0 done,
+// -1 not applicable, >0 error.  On one GPU the ghost rows are refreshed here.
+int fused_sweep(spk_cuda_handle *h, int part) {
   if (!h->tiled || !h->use_fused || h->dim != 2 || !h->fused2d_ok) return -1;
   SweepArgs a;
   a.spin = h->spin; a.g = h->g; a.c0 = 0; a.nloop = 1; a.ev = h->ev;
@@ -309,12 +325,12 @@ int fused_sweep(spk_cuda_handle *h) {
   if (h->d.nranks == 1 && refresh_ghosts_local(h)) return 1;
   int rc;
   switch (h->d.lattice) {
-    case SPK_SQ_4N: rc = fused_sweep_l<SPK_SQ_4N>(h, a); break;
-    case SPK_SQ_8N: rc = fused_sweep_l<SPK_SQ_8N>(h, a); break;
-    case SPK_TRI: rc = fused_sweep_l<SPK_TRI>(h, a); break;
+    case SPK_SQ_4N: rc = fused_sweep_l<SPK_SQ_4N>(h, a, part); break;
+    case SPK_SQ_8N: rc = fused_sweep_l<SPK_SQ_8N>(h, a, part); break;
+    case SPK_TRI: rc = fused_sweep_l<SPK_TRI>(h, a, part); break;
     default: rc = -1;
   }
-  if (rc == 0) h->nattempt += h->nlocal;
+  if (rc == 0 && part != 1) h->nattempt += h->nlocal;
   return rc;
 }
 
@@ -662,8 +678,16 @@ int spk_cuda_sweep_color_strict(spk_cuda_handle *h, int color, const int32_t *bo
   return sweep_set(h, RNG_STRICT, color, box, nloop);
 }
 
+static int halo_exchange_on(spk_cuda_handle *h, cudaStream_t st);
+
 int spk_cuda_halo_exchange(spk_cuda_handle *h) {
   if (!h) return fail("null handle");
+  return halo_exchange_on(h, h->stream);
+}
+
+// ghost layers <- ring neighbours, enqueued on stream `st` (the compute stream for the plain API,
+// the communication stream when spk_cuda_sweeps overlaps the exchange with interior updates)
+static int halo_exchange_on(spk_cuda_handle *h, cudaStream_t st) {
   if (h->d.nranks == 1) return 0;  // periodic images are read in place (Geo::lo_wrap / hi_wrap)
   if (!h->comm) return fail("spk_cuda_comm_init has not been called");
   CU(cudaSetDevice(h->d.device));
@@ -674,12 +698,70 @@ int spk_cuda_halo_exchange(spk_cuda_handle *h) {
   // the exchange runs on the compute stream's timeline: it must see the previous colour's
   // writes and the next colour kernel must see the ghosts
   NC(g_nccl.GroupStart());
-  NC(g_nccl.Send(first, n, ncclInt32, lower, h->comm, h->stream));
-  NC(g_nccl.Send(last, n, ncclInt32, upper, h->comm, h->stream));
-  NC(g_nccl.Recv(ghost_hi, n, ncclInt32, upper, h->comm, h->stream));
-  NC(g_nccl.Recv(ghost_lo, n, ncclInt32, lower, h->comm, h->stream));
+  NC(g_nccl.Send(first, n, ncclInt32, lower, h->comm, st));
+  NC(g_nccl.Send(last, n, ncclInt32, upper, h->comm, st));
+  NC(g_nccl.Recv(ghost_hi, n, ncclInt32, upper, h->comm, st));
+  NC(g_nccl.Recv(ghost_lo, n, ncclInt32, lower, h->comm, st));
   NC(g_nccl.GroupEnd());
   h->launches++;
+  return 0;
+}
+
+// Multi-GPU sweeps with the ghost exchange overlapped with interior updates: the
+// part of a colour set (3-D: first / last plane; 2-D: first / last tile row of the fused sweep)
+// that the neighbours' ghosts depend on is launched first; the exchange of its result runs on the
+// communication stream while the compute stream updates the interior; the next boundary launch
+// waits for the exchange.  Same launches in the same dependency order as the serial schedule,
+// hence the same spins.
+static int sweeps_overlapped(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
+  const bool fused2d = h->dim == 2;
+  auto exchange = [&]() -> int {  // comm stream: after the boundary launch, before the next one
+    CU(cudaEventRecord(h->ev_compute, h->stream));
+    CU(cudaStreamWaitEvent(h->comm_stream, h->ev_compute, 0));
+    int rc = halo_exchange_on(h, h->comm_stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev_halo, h->comm_stream));
+    return 0;
+  };
+  int rc = exchange();  // ghosts for the first boundary launch
+  if (rc) return rc;
+  const int32_t lo_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0, h->g.g0 + 1};
+  const int32_t hi_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0 + h->nslab - 1, h->g.g0 + h->nslab};
+  const int32_t in_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0 + 1, h->g.g0 + h->nslab - 1};
+  for (int s = 0; s < nsweeps; s++) {
+    h->ev.sweep = first_sweep + (uint32_t)s;
+    if (fused2d) {
+      CU(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+      rc = fused_sweep(h, 1);  // first + last tile row -> destination buffer
+      if (rc) return rc > 0 ? fail("fused sweep launch failed") : fail("fused sweep not applicable");
+      // the exchange must move the DESTINATION buffer's boundary rows: swap happens in part 2, so
+      // enqueue the interior first (it swaps the handle's buffers), then exchange the new lattice
+      CU(cudaEventRecord(h->ev_compute, h->stream));
+      rc = fused_sweep(h, 2);
+      if (rc) return fail("fused sweep launch failed");
+      CU(cudaStreamWaitEvent(h->comm_stream, h->ev_compute, 0));
+      rc = halo_exchange_on(h, h->comm_stream);
+      if (rc) return rc;
+      CU(cudaEventRecord(h->ev_halo, h->comm_stream));
+      continue;
+    }
+    for (int color = 1; color <= h->nc; color++) {
+      CU(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+      rc = sweep_set(h, RNG_PHILOX, color, lo_box, 1);
+      if (rc) return rc;
+      if (h->nslab > 1) {
+        rc = sweep_set(h, RNG_PHILOX, color, hi_box, 1);
+        if (rc) return rc;
+      }
+      rc = exchange();
+      if (rc) return rc;
+      if (h->nslab > 2) {
+        rc = sweep_set(h, RNG_PHILOX, color, in_box, 1);
+        if (rc) return rc;
+      }
+    }
+  }
+  CU(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));  // later work on the compute stream sees the ghosts
   return 0;
 }
 
@@ -687,13 +769,20 @@ int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
   if (!h) return fail("null handle");
   if (nsweeps < 0) return fail("nsweeps must be >= 0");
   CU(cudaSetDevice(h->d.device));
+  const bool fused2d = h->tiled && h->use_fused && h->dim == 2 && h->fused2d_ok;
+  // 3-D: 8 (2) exchanges per sweep, worth hiding.  2-D: one exchange of 4 rows per fused sweep; splitting
+  // the single launch into boundary + interior launches costs more than the exchange it hides
+  // (measured: 502 vs 538 Gsites/s at 2 GPUs), so it stays serial unless SPK_CUDA_OVERLAP_2D=1.
+  const bool overlap = h->dim == 3 || (fused2d && getenv("SPK_CUDA_OVERLAP_2D"));
+  if (h->d.nranks > 1 && h->comm && nsweeps > 0 && overlap && !getenv("SPK_CUDA_NO_OVERLAP"))
+    return sweeps_overlapped(h, first_sweep, nsweeps);
   for (int s = 0; s < nsweeps; s++) {
     h->ev.sweep = first_sweep + (uint32_t)s;
-    if (h->tiled && h->use_fused && h->dim == 2 && h->fused2d_ok) {
+    if (fused2d) {
       // 2-D: one launch per sweep; ghost rows (one per fused colour step) are refreshed once
       int rc = spk_cuda_halo_exchange(h);
       if (rc) return rc;
-      rc = fused_sweep(h);
+      rc = fused_sweep(h, 0);
       if (rc == 0) continue;
       if (rc > 0) return fail("fused sweep launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }

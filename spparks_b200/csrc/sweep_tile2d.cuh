@@ -43,7 +43,10 @@ template <int LAT> struct Tile2dCfg {
 
 struct Tile2dMap {
   int ntx, nty, items;
-  int gh;  // ghost rows allocated on each side of the slab (tensor row 0 = lowest ghost row)
+  int gh;      // ghost rows allocated on each side of the slab (tensor row 0 = lowest ghost row)
+  // tile rows of this launch: ty0, ty0+1, ... (ty_run of them), except that run index 1 is
+  // ty_alt when ty_alt >= 0 (the multi-GPU path launches the first and last tile row on their own)
+  int ty0, ty_run, ty_alt;
 };
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
@@ -138,7 +141,8 @@ sweep_tile2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
   uint32_t phase = 0;
   int accepted = 0;
   for (int item = blockIdx.x; item < tm.items; item += gridDim.x) {
-    const int tx = item % tm.ntx, ty = item / tm.ntx;
+    const int tx = item % tm.ntx, trun = item / tm.ntx;
+    const int ty = (tm.ty_alt >= 0 && trun == 1) ? tm.ty_alt : tm.ty0 + trun;
     const int xo = tx * C::OW, yo = ty * T2_OH;     // interior origin (element, owned row)
     const int xb = xo - C::HX, yb = yo - C::HY;     // box origin
     if (tid == 0) {
