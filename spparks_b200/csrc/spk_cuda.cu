@@ -100,6 +100,7 @@ struct spk_cuda_handle {
   ncclComm_t comm = nullptr;
   bool tiled = true;  // tuned kernels allowed (SPK_CUDA_FORCE_GENERIC=1 disables, for A/B tests)
   bool use_stream = true;  // SPK_CUDA_NO_STREAM=1 keeps the strip kernel (A/B tests)
+  bool smem_attr_set[2] = {false, false};  // dynamic shared memory opt-in done for the tile2d / stream kernel
   bool stream_ok = false;  // TMA streaming kernel usable (3-D lattice, tensor map built)
   CUtensorMap tmap;        // (x, y, plane incl. the two ghost planes) view of the slab
   int32_t *base_alt = nullptr;  // second lattice buffer of the out-of-place fused 2-D sweep
@@ -282,12 +283,11 @@ int launch_tile2d(spk_cuda_handle *h, const SweepArgs &a, int part) {
       }
       return 0;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!h->smem_attr_set[0]) {  // per handle: the attribute belongs to the device the handle lives on
       if (cudaFuncSetAttribute(sweep_tile2d_kernel<LAT, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                C::SMEM_BYTES) != cudaSuccess)
         return 1;
-      attr_set = true;
+      h->smem_attr_set[0] = true;
     }
     const int grid_max = 3 * 148;
     const int grid = tm.items < grid_max ? tm.items : grid_max;
@@ -364,20 +364,14 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a) {
     sm.nzc = (nq + sm.qchunk - 1) / sm.qchunk;
     sm.items = sm.ntx * sm.nty * sm.nzc;
     const int grid = sm.items < grid_max ? sm.items : grid_max;
-    SweepArgs args = a;
-    if (h->d.nranks == 1) {  // the kernel reads the slab dimension through the ghost planes
-      if (refresh_ghosts_local(h)) return 1;
-      args.g.lo_wrap = -1;
-      args.g.hi_wrap = h->nslab;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
+    SweepArgs args = a;  // Geo::lo_wrap / hi_wrap select periodic images (1 GPU) or ghost planes (slabs)
+    if (!h->smem_attr_set[1]) {
       if (cudaFuncSetAttribute(sweep_stream_kernel<LAT, MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                C::SMEM_BYTES) != cudaSuccess ||
           cudaFuncSetAttribute(sweep_stream_kernel<LAT, MODEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                C::SMEM_BYTES) != cudaSuccess)
         return 1;
-      attr_set = true;
+      h->smem_attr_set[1] = true;
     }
     if (args.nloop == 1)
       sweep_stream_kernel<LAT, MODEL, true><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, args, sm);

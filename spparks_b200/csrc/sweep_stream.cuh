@@ -11,8 +11,8 @@
 //
 // TMA zero-fills box elements outside the tensor; the periodic images that fall there (x and y
 // edges of the lattice only) are patched in shared memory with plain loads after the box has
-// landed.  The z direction never leaves the tensor: it includes the two ghost planes of the slab
-// (refreshed before each colour by spk_cuda_halo_exchange, also on a single GPU).
+// landed.  The z direction never leaves the tensor: plane -1 / Z is the periodic image (one GPU)
+// or the slab's ghost plane (multi-GPU, refreshed by spk_cuda_halo_exchange), chosen by Geo::lo_wrap / hi_wrap.
 #pragma once
 #include <cuda.h>
 #include "sweep_tiled.cuh"
@@ -202,10 +202,13 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
   }
   __syncthreads();
 
+  // plane kk in -1..Z -> plane that holds it: the periodic image on one GPU (lo_wrap = Z-1,
+  // hi_wrap = 0), the ghost plane of the slab otherwise (lo_wrap = -1, hi_wrap = Z)
+  auto zmap = [&](int kk) { return kk < 0 ? g.lo_wrap : (kk >= g.Z ? g.hi_wrap : kk); };
   auto issue = [&](int kk, uint32_t seq, int x0, int y0) {  // plane kk (local, -1..Z) as sequence number seq
     uint64_t *bar = &full[seq % C::RING];
     mbar_expect_tx(bar, C::PLANE_BYTES);
-    tma_load_3d(plane_ptr(seq), &tmap, bar, x0 - 4, y0 - 1, kk + 1);  // tensor plane 0 = lower ghost plane
+    tma_load_3d(plane_ptr(seq), &tmap, bar, x0 - 4, y0 - 1, zmap(kk) + 1);  // tensor plane 0 = lower ghost plane
   };
   auto wait = [&](uint32_t seq) { mbar_wait(&full[seq % C::RING], (seq / C::RING) & 1u); };
 
@@ -225,7 +228,7 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     if (edge) {  // prologue: the three planes of the first stencil window
       int pv0[3][2];
       for (int p = 0; p < 3; p++)
-        patch_load<LAT>(pp, a.spin + (long long)(kstart - 1 + p) * sz, x0, y0, rowlen, Y, tid, pv0[p]);
+        patch_load<LAT>(pp, a.spin + (long long)zmap(kstart - 1 + p) * sz, x0, y0, rowlen, Y, tid, pv0[p]);
       for (int p = 0; p < 3; p++) {
         wait(Q + p);
         patch_store<LAT>(pp, plane_ptr(Q + p), tid, pv0[p]);
@@ -255,7 +258,7 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           for (int p = 0; p < C::KSTEP; p++) issue(k + 2 + p, Qs + 3 + p, x0, y0);
         if (edge)
           for (int p = 0; p < C::KSTEP; p++)
-            patch_load<LAT>(pp, a.spin + (long long)(k + 2 + p) * sz, x0, y0, rowlen, Y, tid, pv[p]);
+            patch_load<LAT>(pp, a.spin + (long long)zmap(k + 2 + p) * sz, x0, y0, rowlen, Y, tid, pv[p]);
       }
 
       const int32_t *const pl[3] = {plane_ptr(Qs), plane_ptr(Qs + 1), plane_ptr(Qs + 2)};
