@@ -86,6 +86,11 @@ struct EventParams {
   uint32_t sweep;           // Philox counter word 2
   uint32_t thr[27];         // Philox mode: floor(exp(-dE/T) * 2^32), dE = 1..26 (host libm)
   double ptab[27];          // double modes: exp((double)(-dE) * t_inverse)       (host libm)
+  // packed 16-bit path (pk16 below): multipliers kept opaque to the compiler so that the packing
+  // arithmetic stays IMAD (FMA pipe) instead of LEA/PRMT/SHF (ALU pipe, which the compares saturate)
+  int m65536;               // -65536
+  uint32_t rep;             // 0x00010001
+  uint32_t pow2[16];        // 1 << n
 };
 
 // Source of the (at most) two uniforms of one event; the double modes draw lazily like
@@ -115,6 +120,75 @@ template <int NN> __device__ __forceinline__ int unlike(const int (&v)[NN], int 
   return NN > 1 ? e[0] + e[1] : e[0];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed 16-bit compares (all spins of the lattice <= PK16_MAX_SPIN): VIADDMNMX.U16x2, the DPX
+// "add then min" instruction of sm_90+, does TWO equality tests and their accumulation in one
+// ALU-pipe instruction:  min(a + b, acc) per halfword with a = (x, x), b = (-y0, -y1) mod 2^16
+// leaves a zero halfword exactly where x == y.  The 32-bit ISETP form costs one instruction per
+// test on the same pipe (measured with tools/ubench: both 1.5 cycles per warp instruction per
+// SMSP, and no compare instruction of sm_100 runs on the FMA pipe).
+//
+// Encoding: a neighbour pair (lo, hi) is stored as the 32-bit NEGATIVE of (hi << 16 | lo): its low
+// halfword is -lo, its high halfword -hi - 1 (lo >= 1 always borrows); the "+1" is put into the
+// replicated operand instead, rep(x) = (x + 1) << 16 | x, hence the x <= 65534 limit.
+constexpr int PK16_MAX_SPIN = 65534;
+
+__device__ __forceinline__ uint32_t pk_rep(int x, const EventParams &p) { return (uint32_t)x * p.rep + 0x10000u; }
+__device__ __forceinline__ uint32_t pk_negpair(int lo, int hi, const EventParams &p) {
+  return (uint32_t)(hi * p.m65536 - lo);
+}
+// number of neighbours unlike `value` from the packed pairs: min(x - y, 1) per halfword, summed
+// with packed IMADs
+template <int NN> __device__ __forceinline__ int unlike16(const uint32_t (&negp)[NN / 2], int value, const EventParams &p) {
+  static_assert(NN % 2 == 0, "packed path needs an even stencil");
+  const uint32_t a = pk_rep(value, p);
+  uint32_t e[2];
+#pragma unroll
+  for (int j = 0; j < NN / 2; j++) {
+    const uint32_t t = __viaddmin_u16x2(a, negp[j], 0x00010001u);
+    if (j < 2) e[j] = t;
+    else e[j & 1] = t * (uint32_t)p.one + e[j & 1];
+  }
+  const uint32_t s = NN > 2 ? e[0] + e[1] : e[0];
+  return (int)((s & 0xFFFFu) + (s >> 16));
+}
+// first_occurrence_mask (dedupe_chain.cuh) on packed pairs: slot n is tested against the pairs of
+// the earlier slots plus (old, old) [n even] or (v[n-1], old) [n odd]; the chain starts at (1, 1)
+// so that it ends as 0x00010001 exactly when every test was "unequal".  The 0/1 halfwords of all
+// slots are gathered by IMADs (halfword bit n = slot n, 16 slots per accumulator) and ANDed.
+template <int NN>
+__device__ __forceinline__ uint32_t first_occurrence_mask16(const int (&v)[NN], const uint32_t (&negp)[NN / 2], int old,
+                                                             const EventParams &p) {
+  const uint32_t negoo = pk_negpair(old, old, p);
+  uint32_t sum[2] = {0u, 0u};
+#pragma unroll
+  for (int n = 0; n < NN; n++) {
+    const uint32_t a = pk_rep(v[n], p);
+    uint32_t acc = 0x00010001u;
+#pragma unroll
+    for (int j = 0; j < n / 2; j++) acc = __viaddmin_u16x2(a, negp[j], acc);
+    acc = __viaddmin_u16x2(a, (n & 1) ? pk_negpair(v[n - 1], old, p) : negoo, acc);
+    sum[n >> 4] = acc * p.pow2[n & 15] + sum[n >> 4];
+  }
+  uint32_t first = sum[0] & (sum[0] >> 16);
+  if (NN > 16) first |= (sum[1] & (sum[1] >> 16)) << 16;
+  return first;
+}
+// v[pos] from the packed pairs: select tree over NN/2 words, then the halfword
+template <int NN> __device__ __forceinline__ int select_slot16(const uint32_t (&negp)[NN / 2], int pos) {
+  uint32_t t[16];
+#pragma unroll
+  for (int n = 0; n < 16; n++) t[n] = negp[n < NN / 2 ? n : NN / 2 - 1];
+#pragma unroll
+  for (int bit = 1, len = 16; bit < 5; bit++, len >>= 1) {
+    const bool hi = (pos >> bit) & 1;
+#pragma unroll
+    for (int n = 0; n < len / 2; n++) t[n] = hi ? t[2 * n + 1] : t[2 * n];
+  }
+  const uint32_t pr = 0u - t[0];  // hi << 16 | lo
+  return (int)((pos & 1) ? (pr >> 16) : (pr & 0xFFFFu));
+}
+
 // position of the pick-th (0-based) set bit of m; pick < popc(m)
 __device__ __forceinline__ int nth_set_bit(uint32_t m, int pick) {
   int pos = 0;
@@ -142,19 +216,30 @@ template <int NN> __device__ __forceinline__ int select_slot(const int (&v)[NN],
 
 // One site_event_rejection.  `old` = spin[i], v[] = neighbour spins in reference order.
 // Returns the new spin (== old when rejected or no event).
-template <int MODEL, int RNG, int NN>
+// P16: every spin of the lattice is <= PK16_MAX_SPIN, compares run on packed pairs (see above).
+template <int MODEL, int RNG, int NN, bool P16 = false>
 __device__ __forceinline__ int site_event(const EventParams &p, int old, const int (&v)[NN], Draws<RNG> &d) {
   const int Q = p.nspins;
   if (MODEL == SPK_POTTS_PIN && old > Q) return old;  // pinned: no draw (src/app_potts_pin.cpp:97)
 
-  const int e0 = unlike<NN>(v, old, p.one);
+  constexpr bool PK = P16 && MODEL != SPK_ISING;
+  uint32_t negp[PK ? NN / 2 : 1];
+  if constexpr (PK) {
+#pragma unroll
+    for (int j = 0; j < NN / 2; j++) negp[j] = pk_negpair(v[2 * j], v[2 * j + 1], p);
+  }
+  int e0;
+  if constexpr (PK) e0 = unlike16<NN>(negp, old, p);
+  else e0 = unlike<NN>(v, old, p.one);
   int trial;
 
   if constexpr (MODEL == SPK_POTTS_NEIGHONLY) {
     // candidates = distinct neighbour values != old, first-occurrence order
     // (src/app_potts_neighonly.cpp:81-88); bit n of `first` marks slot n as a new candidate
     if (e0 == 0) return old;  // nevent == 0: no draw (src/app_potts_neighonly.cpp:90)
-    const uint32_t first = first_occurrence_mask<NN>(v, old);
+    uint32_t first;
+    if constexpr (PK) first = first_occurrence_mask16<NN>(v, negp, old, p);
+    else first = first_occurrence_mask<NN>(v, old);
     const int nevent = __popc(first);
     int pick;
     if constexpr (RNG == RNG_PHILOX) {
@@ -166,7 +251,8 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
       pick = (int)(nevent * u);
       if (pick >= nevent) pick = nevent - 1;
     }
-    trial = select_slot<NN>(v, nth_set_bit(first, pick));
+    if constexpr (PK) trial = select_slot16<NN>(negp, nth_set_bit(first, pick));
+    else trial = select_slot<NN>(v, nth_set_bit(first, pick));
   } else if constexpr (RNG == RNG_PHILOX) {
     if (MODEL == SPK_ISING) trial = (d.w1 < 0x80000000u) ? 1 : 2;
     else trial = (int)__umulhi((uint32_t)Q, d.w1) + 1;
@@ -206,7 +292,9 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
       return u > p.ptab[dE2] ? old : trial;
     }
   }
-  const int e1 = unlike<NN>(v, trial, p.one);
+  int e1;
+  if constexpr (PK) e1 = unlike16<NN>(negp, trial, p);
+  else e1 = unlike<NN>(v, trial, p.one);
   if (e1 <= e0) return trial;
   if (p.t_zero) return old;
   const int dE = e1 - e0;

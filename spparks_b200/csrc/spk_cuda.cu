@@ -100,7 +100,8 @@ struct spk_cuda_handle {
   ncclComm_t comm = nullptr;
   bool tiled = true;  // tuned kernels allowed (SPK_CUDA_FORCE_GENERIC=1 disables, for A/B tests)
   bool use_stream = true;  // SPK_CUDA_NO_STREAM=1 keeps the strip kernel (A/B tests)
-  bool smem_attr_set[2] = {false, false};  // dynamic shared memory opt-in done for the tile2d / stream kernel
+  bool smem_attr_set[5] = {false, false, false, false, false};  // dynamic shared memory opt-in done: [0] tile2d, [1..4] stream variants
+  bool pk16 = false;       // every spin <= PK16_MAX_SPIN: packed 16-bit compares (SPK_CUDA_NO_PK16=1 disables, for A/B tests)
   bool stream_ok = false;  // TMA streaming kernel usable (3-D lattice, tensor map built)
   CUtensorMap tmap;        // (x, y, plane incl. the two ghost planes) view of the slab
   int32_t *base_alt = nullptr;  // second lattice buffer of the out-of-place fused 2-D sweep
@@ -123,6 +124,9 @@ void build_tables(spk_cuda_handle *h) {
     ev.rk.k[2 * r + 1] = ev.k1 + (uint32_t)r * 0xBB67AE85u;
   }
   ev.sweep = 0;
+  ev.m65536 = -65536;
+  ev.rep = 0x00010001u;
+  for (int n = 0; n < 16; n++) ev.pow2[n] = 1u << n;
   const double t_inverse = ev.t_zero ? 0.0 : 1.0 / h->d.temperature;
   for (int dE = 0; dE < 27; dE++) {
     double p = ev.t_zero ? 0.0 : std::exp((0.0 - (double)dE) * t_inverse);
@@ -365,18 +369,23 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a) {
     sm.items = sm.ntx * sm.nty * sm.nzc;
     const int grid = sm.items < grid_max ? sm.items : grid_max;
     SweepArgs args = a;  // Geo::lo_wrap / hi_wrap select periodic images (1 GPU) or ghost planes (slabs)
-    if (!h->smem_attr_set[1]) {
-      if (cudaFuncSetAttribute(sweep_stream_kernel<LAT, MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               C::SMEM_BYTES) != cudaSuccess ||
-          cudaFuncSetAttribute(sweep_stream_kernel<LAT, MODEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               C::SMEM_BYTES) != cudaSuccess)
-        return 1;
-      h->smem_attr_set[1] = true;
-    }
-    if (args.nloop == 1)
-      sweep_stream_kernel<LAT, MODEL, true><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, args, sm);
-    else
-      sweep_stream_kernel<LAT, MODEL, false><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, args, sm);
+    // P16: packed 16-bit compares (event.cuh) when every spin fits; the Ising shortcut has no compares to pack
+    auto launch = [&](auto ONE, auto PK) -> int {
+      constexpr bool one = decltype(ONE)::value, pk = decltype(PK)::value && MODEL != SPK_ISING;
+      auto *kern = sweep_stream_kernel<LAT, MODEL, one, pk>;
+      bool &attr = h->smem_attr_set[1 + (one ? 0 : 1) + (pk ? 2 : 0)];
+      if (!attr) {  // per handle: the attribute belongs to the device the handle lives on
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) return 1;
+        attr = true;
+      }
+      kern<<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, args, sm);
+      return 0;
+    };
+    using T = std::true_type;
+    using F = std::false_type;
+    const int rc = args.nloop == 1 ? (h->pk16 ? launch(T{}, T{}) : launch(T{}, F{}))
+                                   : (h->pk16 ? launch(F{}, T{}) : launch(F{}, F{}));
+    if (rc) return rc;
     h->launches++;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
   }
@@ -509,6 +518,10 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
   h->use_stream = !(ns && ns[0] == '1');
   const char *nf = getenv("SPK_CUDA_NO_FUSED");
   h->use_fused = !(nf && nf[0] == '1');
+  const char *np = getenv("SPK_CUDA_NO_PK16");
+  // spins are 1..Q (potts/pin: Q+1 marks a pinned site, src/app_potts_pin.cpp:81)
+  h->pk16 = !(np && np[0] == '1') && desc->model != SPK_ISING &&
+            (int64_t)desc->nspins + (desc->model == SPK_POTTS_PIN ? 1 : 0) <= PK16_MAX_SPIN;
   build_tables(h);
 
   auto cleanup = [&](int rc) { spk_cuda_destroy(h); return rc; };

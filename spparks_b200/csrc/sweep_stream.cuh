@@ -122,7 +122,7 @@ __device__ __forceinline__ void patch_store(const PatchPlan &pp, int32_t *pl, in
 }
 
 // one class row of one class plane: the thread's 16-byte chunk holds two class sites at P, P+2
-template <int LAT, int MODEL, int P, bool ONEPASS>
+template <int LAT, int MODEL, int P, bool ONEPASS, bool P16>
 __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *const (&pl)[3], int r, int lane,
                                             int32_t *gchunk, unsigned long long gsite0, int xcell) {
   using L = Lat<LAT>;
@@ -169,7 +169,7 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
         d.w1 = h ? blk.z : blk.x;
         d.w2 = h ? blk.w : blk.y;
       }
-      const int nw = site_event<MODEL, RNG_PHILOX, NN>(a.ev, cur[h], v, d);
+      const int nw = site_event<MODEL, RNG_PHILOX, NN, P16>(a.ev, cur[h], v, d);
       accepted += (nw != cur[h]);
       cur[h] = nw;
     });
@@ -182,7 +182,7 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
   return accepted;
 }
 
-template <int LAT, int MODEL, bool ONEPASS>
+template <int LAT, int MODEL, bool ONEPASS, bool P16>
 __global__ void __launch_bounds__(256, 2)
 sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SweepArgs a,
                     const __grid_constant__ StreamMap sm) {
@@ -279,8 +279,8 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           int32_t *gchunk = a.spin + (long long)k * sz + (long long)y * sy + x;
           const unsigned long long gsite0 =
               ((unsigned long long)(k + g.g0) * g.gY + y) * (unsigned long long)g.gX + x;
-          if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS>(a, pl, r, lane, gchunk, gsite0, x);
-          else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS>(a, pl, r, lane, gchunk, gsite0, x);
+          if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS, P16>(a, pl, r, lane, gchunk, gsite0, x);
+          else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS, P16>(a, pl, r, lane, gchunk, gsite0, x);
         }
       }
       __syncthreads();  // planes k-1 (and k) may now be overwritten by the next step's loads

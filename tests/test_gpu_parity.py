@@ -113,17 +113,24 @@ CASES = [
     ("potts", "tri", (252, 66, 1), 9, 0.5),
     ("potts/neighonly", "tri", (124, 10, 1), 4, 0.6),
     ("potts/pin", "sq/8n", (128, 64, 1), 8, 0.8),
+    # largest Q of the packed 16-bit compare path (spins <= 65534) and the first Q beyond it
+    ("potts/neighonly", "sc/26n", (16, 12, 10), 65534, 0.5),
+    ("potts/pin", "sc/26n", (16, 12, 10), 65533, 0.5),
+    ("potts/neighonly", "sc/26n", (16, 12, 10), 65535, 0.5),
+    ("potts/pin", "sc/26n", (16, 12, 10), 65534, 0.5),
 ]
 
 
 @pytest.mark.parametrize("model,lat,n,q,T", CASES, ids=lambda v: str(v).replace(" ", ""))
-@pytest.mark.parametrize("kernel", ["tuned", "strip", "generic"])
+@pytest.mark.parametrize("kernel", ["tuned", "tuned32", "strip", "generic"])
 def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, kernel, monkeypatch):
     """Production (Philox) mode, three full sweeps, through every kernel family (TMA streaming
-    kernel where it applies, strip kernel, generic kernel): bit-exact against the oracle
-    evaluating the same counter-based stream."""
+    kernel where it applies — with packed 16-bit and with 32-bit compares —, strip kernel, generic
+    kernel): bit-exact against the oracle evaluating the same counter-based stream."""
     if kernel == "generic":
         monkeypatch.setenv("SPK_CUDA_FORCE_GENERIC", "1")
+    if kernel == "tuned32":
+        monkeypatch.setenv("SPK_CUDA_NO_PK16", "1")
     if kernel == "strip":
         monkeypatch.setenv("SPK_CUDA_NO_STREAM", "1")
         monkeypatch.setenv("SPK_CUDA_NO_FUSED", "1")
@@ -142,6 +149,26 @@ def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, kernel, monkeypa
     assert np.array_equal(s.download(), want)
     assert s.counters() == (nacc, 3 * o.nsites)
     assert s.energy() == o.total_energy(want)
+
+
+@pytest.mark.parametrize("model,q", [("potts/neighonly", 65534), ("potts", 65534), ("potts/pin", 65533)])
+def test_packed16_extreme_spin_values(model, q):
+    """Packed 16-bit compares: few distinct spin values taken from both ends of the 16-bit range
+    (many equal neighbours, halfword borrows and the +1 of the replicated operand all exercised)."""
+    rng = np.random.default_rng(31)
+    n = (24, 16, 12)
+    o = O.Oracle(model, "sc/26n", n[0], n[1], n[2], q, 0.6)
+    palette = np.array([1, 2, 255, 256, 32767, 32768, 65279, 65280, q - 1, q], dtype=np.int32)
+    spins = palette[rng.integers(0, len(palette), size=o.nsites)]
+    if model == "potts/pin":
+        spins[rng.random(o.nsites) < 0.05] = q + 1
+    s = _sweep(model, "sc/26n", n, q, 0.6, seed=2718)
+    s.upload(spins)
+    want = spins.copy()
+    nacc = sum(o.sweep_philox(want, 2718, sw) for sw in range(3))
+    s.sweeps(0, 3)
+    assert np.array_equal(s.download(), want)
+    assert s.counters() == (nacc, 3 * o.nsites)
 
 
 def test_per_colour_calls_equal_fused_sweeps():
