@@ -119,6 +119,11 @@ int spk_cuda_comm_init(spk_cuda_handle *h, const char id[SPK_CUDA_COMM_ID_BYTES]
 /* CommLattice::all() -> perform_swap_site (src/comm_lattice.cpp:137-143, 912-946): refresh both
  * ghost planes from the ring neighbours (or from the periodic image when nranks == 1) */
 int spk_cuda_halo_exchange(spk_cuda_handle *h);
+/* how spk_cuda_sweeps refreshes the ghosts of this handle: 0 = one GPU (periodic images read in
+ * place), 1 = NCCL send/recv per colour step, 2 = peer memory (3-D slabs: the boundary launches
+ * store into the neighbours' ghost planes over NVLink, no exchange step; needs one process per
+ * GPU with CUDA IPC between them, chosen by spk_cuda_comm_init, SPK_CUDA_NO_P2P=1 keeps NCCL) */
+int spk_cuda_halo_mode(const spk_cuda_handle *h);
 
 /* stream control and device timing (CUDA events recorded on the handle's own stream) */
 int spk_cuda_sync(spk_cuda_handle *h);

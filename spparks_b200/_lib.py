@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libspparks_cuda.so")
+# SPK_CUDA_LIB selects another build of the same library (kernel A/B experiments only)
+LIB_PATH = os.environ.get("SPK_CUDA_LIB") or os.path.join(_HERE, "lib", "libspparks_cuda.so")
 
 ISING, POTTS, POTTS_NEIGHONLY, POTTS_PIN = 0, 1, 2, 3
 SQ_4N, SQ_8N, TRI, SC_6N, SC_26N = 2, 3, 4, 5, 6
@@ -21,7 +22,7 @@ SYMBOLS = [
     "spk_cuda_randomize", "spk_cuda_pin_random", "spk_cuda_sweep_color", "spk_cuda_sweep_color_injected",
     "spk_cuda_set_siteseeds", "spk_cuda_get_siteseeds", "spk_cuda_sweep_color_strict", "spk_cuda_sweeps",
     "spk_cuda_counters", "spk_cuda_reset_counters", "spk_cuda_energy", "spk_cuda_comm_id",
-    "spk_cuda_comm_init", "spk_cuda_halo_exchange", "spk_cuda_sync", "spk_cuda_timer_start",
+    "spk_cuda_comm_init", "spk_cuda_halo_exchange", "spk_cuda_halo_mode", "spk_cuda_sync", "spk_cuda_timer_start",
     "spk_cuda_timer_stop", "spk_cuda_launch_count", "spk_cuda_device_spins",
 ]
 
@@ -75,6 +76,7 @@ def load():
     L.spk_cuda_comm_id.argtypes = [C.c_char_p]
     L.spk_cuda_comm_init.argtypes = [vp, C.c_char_p]
     L.spk_cuda_halo_exchange.argtypes = [vp]
+    L.spk_cuda_halo_mode.argtypes = [vp]
     L.spk_cuda_sync.argtypes = [vp]
     L.spk_cuda_timer_start.argtypes = [vp]
     L.spk_cuda_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]

@@ -86,4 +86,32 @@ inline int launch_energy(int lattice, cudaStream_t st, const int32_t *spin, cons
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// ---- peer-memory halo ordering (spk_cuda.cu: sweeps_p2p) --------------------------------------
+// signal: this rank has finished boundary step `value` (its stores into the neighbours' ghost
+// planes were made by the preceding launches of the same stream); written into the neighbours'
+// flag words over NVLink
+__global__ void halo_signal_kernel(uint32_t *to_lower, uint32_t *to_upper, uint32_t value) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(to_lower) = value;
+    *reinterpret_cast<volatile uint32_t *>(to_upper) = value;
+    __threadfence_system();
+  }
+}
+// wait until both neighbours have signalled step >= value; gives up after ~20 s (a neighbour died)
+// and raises flags[2] so that the host reports it instead of hanging the device
+__global__ void halo_wait_kernel(uint32_t *flags, uint32_t value) {
+  if (threadIdx.x == 0) {
+    const volatile uint32_t *f = flags;
+    unsigned long long t0 = 0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int32_t)(f[0] - value) < 0 || (int32_t)(f[1] - value) < 0) {
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > 20000000000ull) { flags[2] = 1; break; }
+    }
+    __threadfence_system();
+  }
+}
+
 }  // namespace spk

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include "../../include/spparks_cuda.h"
 #include "aux_kernels.cuh"
@@ -51,6 +52,7 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 } g_nccl;
 
@@ -63,7 +65,7 @@ int nccl_bind() {
   *(void **)(&g_nccl.name) = dlsym(dl, "nccl" #name);                       \
   if (!g_nccl.name) return fail("NCCL symbol nccl" #name " not found")
   BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(GroupStart); BIND(GroupEnd);
-  BIND(Send); BIND(Recv); BIND(GetErrorString);
+  BIND(Send); BIND(Recv); BIND(AllGather); BIND(GetErrorString);
 #undef BIND
   g_nccl.dl = dl;
   return 0;
@@ -106,6 +108,17 @@ struct spk_cuda_handle {
   CUtensorMap tmap;        // (x, y, plane incl. the two ghost planes) view of the slab
   int32_t *base_alt = nullptr;  // second lattice buffer of the out-of-place fused 2-D sweep
   CUtensorMap tmap_alt;
+  // peer-memory halo (3-D slabs through the streaming kernel): the boundary launches of a colour
+  // store straight into the ring neighbours' ghost planes over NVLink, ordered by flag words
+  bool p2p = false;
+  void *peer_map[2] = {nullptr, nullptr};       // mapped lattice allocations of the lower / upper neighbour
+  void *peer_flag_map[2] = {nullptr, nullptr};  // mapped flag words of the lower / upper neighbour
+  uint32_t *flags = nullptr;      // [0] boundary steps finished by the lower neighbour, [1] by the upper, [2] wait timed out
+  uint32_t *peer_flags[2] = {nullptr, nullptr};  // the words this rank signals: lower's [1], upper's [0]
+  int32_t *mirror_lo = nullptr, *mirror_hi = nullptr;  // lower neighbour's upper ghost plane, upper neighbour's lower ghost plane
+  bool mirror_active = false;     // boundary launches of spk_cuda_sweeps only
+  bool ghosts_valid = false;      // ghost planes hold the neighbours' current boundary planes
+  uint32_t step = 0;              // boundary steps signalled so far (same sequence on every rank)
 };
 
 namespace {
@@ -325,6 +338,7 @@ int fused_sweep(spk_cuda_handle *h, int part) {
   SweepArgs a;
   a.spin = h->spin; a.g = h->g; a.c0 = 0; a.nloop = 1; a.ev = h->ev;
   a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept;
+  a.mirror_lo = a.mirror_hi = nullptr;
   a.b = Box{0, h->g.X, 0, h->g.Y, 0, 1};
   if (h->d.nranks == 1 && refresh_ghosts_local(h)) return 1;
   int rc;
@@ -396,6 +410,8 @@ int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int
   SweepArgs a;
   a.spin = h->spin; a.g = h->g; a.c0 = color - 1; a.nloop = nloop; a.ev = h->ev;
   a.u1 = h->u1; a.u2 = h->u2; a.seeds = h->seeds; a.naccept = h->naccept;
+  a.mirror_lo = h->mirror_active ? h->mirror_lo : nullptr;
+  a.mirror_hi = h->mirror_active ? h->mirror_hi : nullptr;
   if (!local_box(h, box, a.b)) return 0;
   h->nattempt += class_count<LAT>(h, a.b, a.c0) * nloop;
   if (rng == RNG_PHILOX) {
@@ -403,6 +419,7 @@ int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int
       int rc = h->use_stream ? launch_stream<LAT, MODEL>(h, a) : -1;
       if (rc == 0) return 0;
       if (rc > 0) return fail("stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      if (h->mirror_active) return fail("peer-memory halo needs the streaming kernel");
       rc = launch_tiled<LAT, MODEL>(h->stream, a, &h->launches);
       if (rc == 0) return 0;
       if (rc > 0) return fail("tiled kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -425,6 +442,7 @@ template <int LAT> int sweep_set_l(spk_cuda_handle *h, int rng, int color, const
 
 int sweep_set(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
   if (!h) return fail("null handle");
+  if (!h->mirror_active) h->ghosts_valid = false;
   if (color < 1 || color > h->nc) return fail("colour %d out of range 1..%d", color, h->nc);
   if (nloop < 1) return fail("nloop must be >= 1");
   CU(cudaSetDevice(h->d.device));
@@ -568,6 +586,12 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   cudaSetDevice(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  for (int side = 0; side < 2; side++) {
+    if (side == 1 && h->peer_map[1] == h->peer_map[0]) break;
+    if (h->peer_map[side]) cudaIpcCloseMemHandle(h->peer_map[side]);
+    if (h->peer_flag_map[side]) cudaIpcCloseMemHandle(h->peer_flag_map[side]);
+  }
+  cudaFree(h->flags);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->base); cudaFree(h->base_alt); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
   if (h->t0) cudaEventDestroy(h->t0);
@@ -589,6 +613,7 @@ int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n) {
   CU(cudaSetDevice(h->d.device));
   CU(cudaMemcpyAsync(h->spin, host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  h->ghosts_valid = false;
   return 0;
 }
 
@@ -617,6 +642,7 @@ int spk_cuda_randomize(spk_cuda_handle *h, uint64_t seed, int32_t lo, int32_t hi
   CU(cudaSetDevice(h->d.device));
   const int64_t goff = (int64_t)h->g.g0 * h->plane;
   randomize_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, goff, seed, lo, (uint32_t)(hi - lo + 1));
+  h->ghosts_valid = false;
   h->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -631,6 +657,7 @@ int spk_cuda_pin_random(spk_cuda_handle *h, uint64_t seed, double fraction) {
   double t = std::floor(fraction * 4294967296.0);
   const uint32_t thr = t > 4294967295.0 ? 4294967295u : (uint32_t)t;
   pin_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, goff, seed, thr, h->d.nspins + 1);
+  h->ghosts_valid = false;
   h->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -686,10 +713,13 @@ int spk_cuda_sweep_color_strict(spk_cuda_handle *h, int color, const int32_t *bo
 }
 
 static int halo_exchange_on(spk_cuda_handle *h, cudaStream_t st);
+static int check_halo_timeout(spk_cuda_handle *h);
 
 int spk_cuda_halo_exchange(spk_cuda_handle *h) {
   if (!h) return fail("null handle");
-  return halo_exchange_on(h, h->stream);
+  const int rc = halo_exchange_on(h, h->stream);
+  if (rc == 0) h->ghosts_valid = true;
+  return rc;
 }
 
 // ghost layers <- ring neighbours, enqueued on stream `st` (the compute stream for the plain API,
@@ -772,10 +802,53 @@ static int sweeps_overlapped(spk_cuda_handle *h, uint32_t first_sweep, int nswee
   return 0;
 }
 
+// Multi-GPU sweeps over peer memory (3-D slabs): no exchange step at all.  Per colour the compute
+// stream runs   wait(neighbours finished boundary step t-1)  ->  boundary launches, which store
+// their updates locally AND into the neighbours' ghost planes  ->  signal(step t) into the
+// neighbours' flag words  ->  interior launch (reads no ghost plane, so the neighbours' stores for
+// step t land while it runs).  wait(t-1) covers both hazards: the ghosts this rank reads are
+// complete (RAW), and the neighbour has finished reading the ghost this rank is about to overwrite
+// (WAR; within one step the planes a colour updates and the ghost planes it reads have opposite
+// parity, so same-step launches never touch the same words).
+static int sweeps_p2p(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
+  if (!h->ghosts_valid) {  // spins changed outside spk_cuda_sweeps: one NCCL exchange re-seeds the ghosts
+    int rc = halo_exchange_on(h, h->stream);
+    if (rc) return rc;
+  }
+  const int32_t lo_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0, h->g.g0 + 1};
+  const int32_t hi_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0 + h->nslab - 1, h->g.g0 + h->nslab};
+  const int32_t in_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0 + 1, h->g.g0 + h->nslab - 1};
+  int rc = 0;
+  for (int s = 0; s < nsweeps && !rc; s++) {
+    h->ev.sweep = first_sweep + (uint32_t)s;
+    for (int color = 1; color <= h->nc && !rc; color++) {
+      const uint32_t t = ++h->step;
+      halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, t - 1);
+      h->mirror_active = true;
+      rc = sweep_set(h, RNG_PHILOX, color, lo_box, 1);
+      if (!rc) rc = sweep_set(h, RNG_PHILOX, color, hi_box, 1);
+      h->mirror_active = false;
+      halo_signal_kernel<<<1, 32, 0, h->stream>>>(h->peer_flags[0], h->peer_flags[1], t);
+      h->launches += 2;
+      if (!rc && h->nslab > 2) rc = sweep_set(h, RNG_PHILOX, color, in_box, 1);
+    }
+  }
+  // the neighbours' last stores into this rank's ghost planes must have landed before anything
+  // later on the stream reads them (energy, the next call's boundary launches)
+  halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->step);
+  h->launches++;
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  h->ghosts_valid = true;
+  return 0;
+}
+
 int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
   if (!h) return fail("null handle");
   if (nsweeps < 0) return fail("nsweeps must be >= 0");
   CU(cudaSetDevice(h->d.device));
+  if (h->d.nranks > 1 && h->comm && h->p2p && nsweeps > 0 && h->tiled && h->use_stream)
+    return sweeps_p2p(h, first_sweep, nsweeps);
   const bool fused2d = h->tiled && h->use_fused && h->dim == 2 && h->fused2d_ok;
   // 3-D: 8 (2) exchanges per sweep, worth hiding.  2-D: one exchange of 4 rows per fused sweep; splitting
   // the single launch into boundary + interior launches costs more than the exchange it hides
@@ -783,6 +856,22 @@ int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
   const bool overlap = h->dim == 3 || (fused2d && getenv("SPK_CUDA_OVERLAP_2D"));
   if (h->d.nranks > 1 && h->comm && nsweeps > 0 && overlap && !getenv("SPK_CUDA_NO_OVERLAP"))
     return sweeps_overlapped(h, first_sweep, nsweeps);
+  if (h->d.nranks == 1 && h->dim == 3 && getenv("SPK_CUDA_SPLIT_TEST")) {
+    // timing experiment: the boundary / interior launch split of the multi-GPU schedule on one GPU
+    const int32_t lo_box[6] = {0, h->g.gX, 0, h->g.gY, 0, 1};
+    const int32_t hi_box[6] = {0, h->g.gX, 0, h->g.gY, h->nslab - 1, h->nslab};
+    const int32_t in_box[6] = {0, h->g.gX, 0, h->g.gY, 1, h->nslab - 1};
+    for (int s = 0; s < nsweeps; s++) {
+      h->ev.sweep = first_sweep + (uint32_t)s;
+      for (int color = 1; color <= h->nc; color++) {
+        int rc = sweep_set(h, RNG_PHILOX, color, lo_box, 1);
+        if (!rc) rc = sweep_set(h, RNG_PHILOX, color, hi_box, 1);
+        if (!rc) rc = sweep_set(h, RNG_PHILOX, color, in_box, 1);
+        if (rc) return rc;
+      }
+    }
+    return 0;
+  }
   for (int s = 0; s < nsweeps; s++) {
     h->ev.sweep = first_sweep + (uint32_t)s;
     if (fused2d) {
@@ -811,7 +900,7 @@ int spk_cuda_counters(spk_cuda_handle *h, int64_t *naccept, int64_t *nattempt) {
   CU(cudaStreamSynchronize(h->stream));
   if (naccept) *naccept = (int64_t)acc;
   if (nattempt) *nattempt = h->nattempt;
-  return 0;
+  return check_halo_timeout(h);
 }
 
 int spk_cuda_reset_counters(spk_cuda_handle *h) {
@@ -837,6 +926,70 @@ int spk_cuda_energy(spk_cuda_handle *h, double *energy) {
   return 0;
 }
 
+// Map the ring neighbours' lattice allocations and flag words (CUDA IPC; one process per GPU) for
+// the peer-memory halo.  The handles travel through one ncclAllGather; a second one makes every
+// rank agree on whether the mapping worked everywhere (otherwise all keep the NCCL exchange).
+static int setup_p2p(spk_cuda_handle *h) {
+  struct Ipc { cudaIpcMemHandle_t base, flags; int ok; int pad[3]; };
+  h->p2p = false;
+  const char *np = getenv("SPK_CUDA_NO_P2P");
+  const int want = h->dim == 3 && h->stream_ok && h->nslab >= 2 && !(np && np[0] == '1');
+  const int n = h->d.nranks, lower = (h->d.rank + n - 1) % n, upper = (h->d.rank + 1) % n;
+  Ipc mine;
+  memset(&mine, 0, sizeof mine);
+  if (want) {
+    if (!h->flags) {
+      CU(cudaMalloc(&h->flags, 4 * sizeof(uint32_t)));
+      CU(cudaMemset(h->flags, 0, 4 * sizeof(uint32_t)));
+    }
+    mine.ok = cudaIpcGetMemHandle(&mine.base, h->base) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.flags, h->flags) == cudaSuccess;
+    cudaGetLastError();
+  }
+  Ipc *dev = nullptr;
+  CU(cudaMalloc(&dev, (size_t)(n + 1) * sizeof(Ipc)));
+  std::vector<Ipc> all(n);
+  auto gather = [&]() -> int {
+    CU(cudaMemcpyAsync(dev + n, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllGather(dev + n, dev, sizeof(Ipc), ncclChar, h->comm, h->stream));
+    CU(cudaMemcpyAsync(all.data(), dev, (size_t)n * sizeof(Ipc), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+  };
+  int rc = gather();
+  bool every = rc == 0;
+  for (int r = 0; r < n && every; r++) every = all[r].ok != 0;
+  if (every) {  // open the neighbours' allocations (one mapping when both neighbours are the same rank)
+    const int peers[2] = {lower, upper};
+    for (int side = 0; side < 2 && mine.ok; side++) {
+      if (side == 1 && upper == lower) {
+        h->peer_map[1] = h->peer_map[0];
+        h->peer_flag_map[1] = h->peer_flag_map[0];
+        continue;
+      }
+      if (cudaIpcOpenMemHandle(&h->peer_map[side], all[peers[side]].base, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&h->peer_flag_map[side], all[peers[side]].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        mine.ok = 0;
+      }
+    }
+    rc = gather();  // agreement round
+    every = rc == 0;
+    for (int r = 0; r < n && every; r++) every = all[r].ok != 0;
+  }
+  cudaFree(dev);
+  if (rc) return rc;
+  if (every) {
+    // lower neighbour's UPPER ghost plane mirrors my plane 0; upper neighbour's LOWER ghost plane my last plane
+    h->mirror_lo = (int32_t *)h->peer_map[0] + (int64_t)(h->gh + h->nslab) * h->plane;
+    h->mirror_hi = (int32_t *)h->peer_map[1];
+    h->peer_flags[0] = (uint32_t *)h->peer_flag_map[0] + 1;  // I am the lower neighbour's upper neighbour
+    h->peer_flags[1] = (uint32_t *)h->peer_flag_map[1] + 0;
+    h->p2p = true;
+  }
+  return 0;
+}
+
 int spk_cuda_comm_id(char id[SPK_CUDA_COMM_ID_BYTES]) {
   static_assert(sizeof(ncclUniqueId) <= SPK_CUDA_COMM_ID_BYTES, "ncclUniqueId larger than the ABI buffer");
   if (!id) return fail("null argument");
@@ -857,7 +1010,22 @@ int spk_cuda_comm_init(spk_cuda_handle *h, const char id[SPK_CUDA_COMM_ID_BYTES]
   ncclUniqueId u;
   memcpy(&u, id, sizeof u);
   NC(g_nccl.CommInitRank(&h->comm, h->d.nranks, u, h->d.rank));
+  return setup_p2p(h);
+}
+
+// the peer-memory halo's device-side wait gave up: a ring neighbour never signalled its step
+static int check_halo_timeout(spk_cuda_handle *h) {
+  if (!h->p2p) return 0;
+  uint32_t timed_out = 0;
+  CU(cudaMemcpyAsync(&timed_out, h->flags + 2, sizeof timed_out, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (timed_out) return fail("peer-memory halo: a neighbour rank did not signal its boundary step within 20 s");
   return 0;
+}
+
+int spk_cuda_halo_mode(const spk_cuda_handle *h) {
+  if (!h || h->d.nranks == 1) return 0;
+  return (h->p2p && h->tiled && h->use_stream) ? 2 : 1;
 }
 
 int spk_cuda_sync(spk_cuda_handle *h) {
@@ -865,7 +1033,7 @@ int spk_cuda_sync(spk_cuda_handle *h) {
   CU(cudaSetDevice(h->d.device));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaStreamSynchronize(h->comm_stream));
-  return 0;
+  return check_halo_timeout(h);
 }
 
 int spk_cuda_timer_start(spk_cuda_handle *h) {

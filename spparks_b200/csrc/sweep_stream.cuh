@@ -124,7 +124,7 @@ __device__ __forceinline__ void patch_store(const PatchPlan &pp, int32_t *pl, in
 // one class row of one class plane: the thread's 16-byte chunk holds two class sites at P, P+2
 template <int LAT, int MODEL, int P, bool ONEPASS, bool P16>
 __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *const (&pl)[3], int r, int lane,
-                                            int32_t *gchunk, unsigned long long gsite0, int xcell) {
+                                            int32_t *gchunk, int32_t *gmirror, unsigned long long gsite0, int xcell) {
   using L = Lat<LAT>;
   constexpr int NN = L::NN;
   using R = RowInfo<LAT, 0>;
@@ -177,13 +177,18 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
   if (cur[0] != before0 || cur[1] != before1) {
     W[4][1 + P] = cur[0];
     W[4][3 + P] = cur[1];
-    *reinterpret_cast<int4 *>(gchunk) = make_int4(W[4][1], W[4][2], W[4][3], W[4][4]);
+    const int4 nv = make_int4(W[4][1], W[4][2], W[4][3], W[4][4]);
+    *reinterpret_cast<int4 *>(gchunk) = nv;
+    if (gmirror) *reinterpret_cast<int4 *>(gmirror) = nv;  // the neighbour's ghost copy of this chunk
   }
   return accepted;
 }
 
 template <int LAT, int MODEL, bool ONEPASS, bool P16>
-__global__ void __launch_bounds__(256, 2)
+#ifndef ST_MINB
+#define ST_MINB 2
+#endif
+__global__ void __launch_bounds__(256, (MODEL == SPK_POTTS_NEIGHONLY && P16) ? ST_MINB : 2)
 sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SweepArgs a,
                     const __grid_constant__ StreamMap sm) {
   using C = StreamCfg<LAT>;
@@ -277,10 +282,13 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         if (y < Y && x < rowlen) {  // y: warp-uniform
           const int r = y - y0 + 1;
           int32_t *gchunk = a.spin + (long long)k * sz + (long long)y * sy + x;
+          int32_t *gmirror = nullptr;  // k: CTA-uniform
+          if (k == 0 && a.mirror_lo) gmirror = a.mirror_lo + (long long)y * sy + x;
+          if (k == g.Z - 1 && a.mirror_hi) gmirror = a.mirror_hi + (long long)y * sy + x;
           const unsigned long long gsite0 =
               ((unsigned long long)(k + g.g0) * g.gY + y) * (unsigned long long)g.gX + x;
-          if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS, P16>(a, pl, r, lane, gchunk, gsite0, x);
-          else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS, P16>(a, pl, r, lane, gchunk, gsite0, x);
+          if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x);
+          else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x);
         }
       }
       __syncthreads();  // planes k-1 (and k) may now be overwritten by the next step's loads

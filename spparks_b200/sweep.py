@@ -131,6 +131,10 @@ class LatticeSweep:
     def halo_exchange(self):
         _lib.check(self.L.spk_cuda_halo_exchange(self.h))
 
+    def halo_mode(self):
+        """0 = single GPU, 1 = NCCL exchange per colour step, 2 = peer-memory stores (no exchange)."""
+        return int(self.L.spk_cuda_halo_mode(self.h))
+
     # -- stream / timing -----------------------------------------------------------------------
     def sync(self):
         _lib.check(self.L.spk_cuda_sync(self.h))

@@ -1,4 +1,5 @@
-"""Worker for tests/test_multigpu.py (run under torchrun, one rank per GPU).
+"""Worker for tests/test_multigpu.py (run under torchrun, one rank per GPU).  SPK_CUDA_NO_P2P=1
+in the environment keeps the NCCL exchange for the 3-D cases (default: peer-memory halo).
 
 Checks that an N-slab run (ghost planes exchanged with NCCL before every colour, as
 CommLattice::all() does, src/app_lattice.cpp:650-651) reproduces the 1-GPU run spin for spin, for
@@ -46,9 +47,12 @@ def main():
             idt = torch.frombuffer(bytearray(LatticeSweep.comm_id()), dtype=torch.uint8).cuda()
         dist.broadcast(idt, 0)
         s.comm_init(idt.cpu().numpy().tobytes())
+        want_mode = 2 if dim3 and os.environ.get("SPK_CUDA_NO_P2P") != "1" else 1
+        assert s.halo_mode() == want_mode, (model, lat, "halo mode", s.halo_mode())
         lo, hi = rank * s.nlocal, (rank + 1) * s.nlocal
         s.upload(spins[lo:hi])
-        s.sweeps(3, 4)
+        s.sweeps(3, 2)
+        s.sweeps(5, 2)  # second call: ghosts are still valid, no re-seeding exchange
         mine = torch.from_numpy(s.download()).cuda()
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)

@@ -81,6 +81,32 @@ def body(kind):
             L.append("add.u16x2 r%d, %%1, %%%d;" % (i % 4, 2 + i % 8))
             L.append("min.u16x2 acc%d, r%d, acc%d;" % (i % 4, i % 4, i % 4))
             L.append("setp.eq.or.s32 p%d, %%1, %%%d, p%d;" % (i % 4, 2 + i % 8, i % 4))
+    elif kind == "viaddmnmx_imm_imad":   # third VIADDMNMX operand immediate (2 register sources)
+        for i in range(UNROLL // 2):
+            L.append("add.u16x2 r%d, acc%d, %%%d;" % (i % 4, i % 4, 2 + i % 8))
+            L.append("min.u16x2 acc%d, r%d, cst;" % (i % 4, i % 4))
+            L.append("mad.lo.s32 s%d, s%d, %%%d, %%1;" % (i % 4, i % 4, 2 + i % 8))
+    elif kind == "viaddmnmx_imad2":   # IMAD with two register sources (multiplier immediate-like constant 3)
+        for i in range(UNROLL // 2):
+            L.append("add.u16x2 r%d, %%1, %%%d;" % (i % 4, 2 + i % 8))
+            L.append("min.u16x2 acc%d, r%d, acc%d;" % (i % 4, i % 4, i % 4))
+            L.append("mad.lo.s32 s%d, s%d, 3, %%1;" % (i % 4, i % 4))
+    elif kind == "lop3_imad":
+        for i in range(UNROLL // 2):
+            L.append("lop3.b32 acc%d, acc%d, %%%d, %%1, 0x96;" % (i % 4, i % 4, 2 + i % 8))
+            L.append("mad.lo.s32 s%d, s%d, %%%d, %%1;" % (i % 4, i % 4, 2 + i % 8))
+    elif kind == "viaddmnmx_ffma":
+        for i in range(UNROLL // 2):
+            L.append("add.u16x2 r%d, %%1, %%%d;" % (i % 4, 2 + i % 8))
+            L.append("min.u16x2 acc%d, r%d, acc%d;" % (i % 4, i % 4, i % 4))
+            L.append("fma.rn.f32 s%d, s%d, %%%d, %%1;" % (i % 4, i % 4, 2 + i % 8))
+    elif kind == "viaddmnmx_2to1":  # 2 VIADDMNMX : 1 IMAD, the ratio of the dedupe code
+        for i in range(21):
+            L.append("add.u16x2 r%d, %%1, %%%d;" % (i % 4, 2 + i % 8))
+            L.append("min.u16x2 acc%d, r%d, acc%d;" % (i % 4, i % 4, i % 4))
+            L.append("add.u16x2 r%d, %%1, %%%d;" % ((i+1) % 4, 2 + (i+1) % 8))
+            L.append("min.u16x2 acc%d, r%d, acc%d;" % ((i+1) % 4, (i+1) % 4, (i+1) % 4))
+            L.append("mad.lo.s32 s%d, s%d, %%%d, %%1;" % (i % 4, i % 4, 2 + i % 8))
     elif kind == "match":
         for i in range(UNROLL // 8):
             L.append("match.any.sync.b32 r%d, acc%d, 0xffffffff;" % (i % 4, i % 4))
@@ -88,7 +114,7 @@ def body(kind):
     return L
 
 KINDS = ["isetp", "fsetp", "hsetp2", "hsetp2_plop", "plop", "hset2bm", "hset2bm_lop", "lop3", "imad",
-         "isetp_hsetp2", "isetp_fsetp", "isetp_hset2bm", "isetp_imad", "hset2bm_imad", "hsetp2_imad", "plop_imad", "viaddmnmx", "viaddmnmx_imad", "viaddmnmx_isetp", "match"]
+         "isetp_hsetp2", "isetp_fsetp", "isetp_hset2bm", "isetp_imad", "hset2bm_imad", "hsetp2_imad", "plop_imad", "viaddmnmx", "viaddmnmx_imad", "viaddmnmx_isetp", "viaddmnmx_imm_imad", "viaddmnmx_imad2", "lop3_imad", "viaddmnmx_ffma", "viaddmnmx_2to1", "match"]
 
 print('#include <cstdio>\n#include <cstdint>\n#include <cuda_runtime.h>')
 for k in KINDS:
@@ -97,7 +123,7 @@ for k in KINDS:
     print("  uint32_t a = in[threadIdx.x], b[8], r = 0;")
     print("  for (int i = 0; i < 8; i++) b[i] = in[256 + i + (threadIdx.x & 1)];")
     print("  long long t0 = clock64();")
-    print("  asm volatile(\"{\\n\\t.reg .pred p<4>, q<4>;\\n\\t.reg .b32 r<4>, s<4>, acc<4>;\\n\\t.reg .s32 it;\\n\\t\"")
+    print("  asm volatile(\"{\\n\\t.reg .pred p<4>, q<4>;\\n\\t.reg .b32 r<4>, s<4>, acc<4>;\\n\\t.reg .s32 it;\\n\\t.reg .b32 cst;\\n\\tmov.b32 cst, 0x00010001;\\n\\t\"")
     for j in range(4):
         print('      "setp.eq.s32 p%d, %%1, %d;\\n\\tsetp.eq.s32 q%d, %%2, %d;\\n\\tmov.b32 acc%d, %%%d;\\n\\tmov.b32 r%d, 0;\\n\\tmov.b32 s%d, 0;\\n\\t"' % (j, j + 77, j, j + 55, j, 2 + j, j, j))
     print('      "mov.s32 it, %%10;\\n\\tLOOP_%s:\\n\\t"' % k)
@@ -118,7 +144,7 @@ print("  cudaMalloc(&in, 4096); cudaMemset(in, 1, 4096); cudaMalloc(&out, nb * 2
 print("  long long *h = new long long[nb];")
 for k in KINDS:
     n = len(body(k))
-    if k.startswith("viaddmnmx"): n = UNROLL
+    if k.startswith("viaddmnmx"): n = sum(1 for o in body(k) if not o.startswith("add.u16x2"))
     print("  for (int rep = 0; rep < 2; rep++) { k_%s<<<nb, 256>>>(in, out, iters, cyc); cudaDeviceSynchronize(); }" % k)
     print("  cudaMemcpy(h, cyc, nb * 8, cudaMemcpyDeviceToHost);")
     print("  { double s = 0; for (int i = 0; i < nb; i++) s += h[i]; s /= nb;")
