@@ -273,6 +273,11 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         cnt = torch.tensor([natt, nacc, launches], dtype=torch.float64, device="cuda")
         if world > 1:
+            per_rank = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(per_rank, t)
+            if rank == 0:
+                print("per-rank ms/step: " + " ".join("%.3f" % (float(x.item()) / steps) for x in per_rank),
+                      file=sys.stderr)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         natt_all, nacc_all, launches_all = [int(v) for v in cnt.tolist()]

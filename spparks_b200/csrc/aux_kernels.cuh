@@ -98,6 +98,29 @@ __global__ void halo_signal_kernel(uint32_t *to_lower, uint32_t *to_upper, uint3
     __threadfence_system();
   }
 }
+// 2-D slabs: copy this rank's first / last ghost-depth rows into the neighbours' ghost rows over
+// NVLink (128-bit stores) and signal the step once every block's stores are out: the last block
+// to finish (device-wide counter `done`, reset for the next push) writes the flags.
+__global__ void __launch_bounds__(1024) halo_push_kernel(const int4 *__restrict__ first, int4 *lower_ghost,
+                                                         const int4 *__restrict__ last, int4 *upper_ghost, long long n16,
+                                                         uint32_t *done, uint32_t *to_lower, uint32_t *to_upper,
+                                                         uint32_t value) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    lower_ghost[i] = first[i];
+    upper_ghost[i] = last[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      *reinterpret_cast<volatile uint32_t *>(to_lower) = value;
+      *reinterpret_cast<volatile uint32_t *>(to_upper) = value;
+      __threadfence_system();
+    }
+  }
+}
 // wait until both neighbours have signalled step >= value; gives up after ~20 s (a neighbour died)
 // and raises flags[2] so that the host reports it instead of hanging the device
 __global__ void halo_wait_kernel(uint32_t *flags, uint32_t value) {

@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library is bound lazily with dlopen (see NcclApi)
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -112,6 +113,8 @@ struct spk_cuda_handle {
   // store straight into the ring neighbours' ghost planes over NVLink, ordered by flag words
   bool p2p = false;
   void *peer_map[2] = {nullptr, nullptr};       // mapped lattice allocations of the lower / upper neighbour
+  void *peer_map_alt[2] = {nullptr, nullptr};   // ... and of their second buffers (2-D ping-pong)
+  int32_t *alloc0 = nullptr;                    // the allocation `base` pointed to at create (the buffers swap per fused sweep, in lockstep on all ranks)
   void *peer_flag_map[2] = {nullptr, nullptr};  // mapped flag words of the lower / upper neighbour
   uint32_t *flags = nullptr;      // [0] boundary steps finished by the lower neighbour, [1] by the upper, [2] wait timed out
   uint32_t *peer_flags[2] = {nullptr, nullptr};  // the words this rank signals: lower's [1], upper's [0]
@@ -556,6 +559,7 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
     cudaGetLastError();
     return cleanup(fail("cudaMalloc of %zu bytes for the lattice failed", bytes));
   }
+  h->alloc0 = h->base;
   h->spin = h->base + (int64_t)h->gh * h->plane;
   if (cudaMemset(h->base, 0, bytes) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
   if (dim == 2 && h->tiled && h->use_fused && (h->plane % 8) == 0) {
@@ -589,6 +593,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   for (int side = 0; side < 2; side++) {
     if (side == 1 && h->peer_map[1] == h->peer_map[0]) break;
     if (h->peer_map[side]) cudaIpcCloseMemHandle(h->peer_map[side]);
+    if (h->peer_map_alt[side]) cudaIpcCloseMemHandle(h->peer_map_alt[side]);
     if (h->peer_flag_map[side]) cudaIpcCloseMemHandle(h->peer_flag_map[side]);
   }
   cudaFree(h->flags);
@@ -843,12 +848,49 @@ static int sweeps_p2p(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
   return 0;
 }
 
+// 2-D slabs (colour-fused sweep, out of place): after each sweep the new boundary rows are pushed
+// into the neighbours' ghost rows of the SAME buffer (the buffers swap in lockstep on all ranks)
+// by one small kernel that also signals the step; wait(t-1) before the sweep kernel orders both the ghosts it reads and the
+// neighbour's last reads of the ghost rows the push overwrites (two sweeps earlier).
+static int sweeps_p2p_2d(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
+  if (!h->ghosts_valid) {
+    int rc = halo_exchange_on(h, h->stream);
+    if (rc) return rc;
+  }
+  const size_t rows = (size_t)h->plane * h->gh;
+  for (int s = 0; s < nsweeps; s++) {
+    h->ev.sweep = first_sweep + (uint32_t)s;
+    const uint32_t t = ++h->step;
+    halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, t - 1);
+    int rc = fused_sweep(h, 0);  // swaps the buffers: h->base is the new lattice
+    if (rc) return rc > 0 ? fail("fused sweep launch failed") : fail("fused sweep not applicable");
+    const bool cur0 = h->base == h->alloc0;
+    int32_t *lower_buf = (int32_t *)(cur0 ? h->peer_map[0] : h->peer_map_alt[0]);
+    int32_t *upper_buf = (int32_t *)(cur0 ? h->peer_map[1] : h->peer_map_alt[1]);
+    const long long n16 = (long long)(rows / 4);  // rows are multiples of 8 elements (fused2d_ok)
+    const int nblk = (int)std::min<long long>(16, (n16 + 1023) / 1024);
+    halo_push_kernel<<<nblk, 1024, 0, h->stream>>>(
+        reinterpret_cast<const int4 *>(h->spin), reinterpret_cast<int4 *>(lower_buf + (int64_t)(h->gh + h->nslab) * h->plane),
+        reinterpret_cast<const int4 *>(h->spin + (int64_t)(h->nslab - h->gh) * h->plane), reinterpret_cast<int4 *>(upper_buf),
+        n16, h->flags + 3, h->peer_flags[0], h->peer_flags[1], t);
+    h->launches += 2;
+  }
+  halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, h->step);
+  h->launches++;
+  CU(cudaGetLastError());
+  h->ghosts_valid = true;
+  return 0;
+}
+
 int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
   if (!h) return fail("null handle");
   if (nsweeps < 0) return fail("nsweeps must be >= 0");
   CU(cudaSetDevice(h->d.device));
-  if (h->d.nranks > 1 && h->comm && h->p2p && nsweeps > 0 && h->tiled && h->use_stream)
-    return sweeps_p2p(h, first_sweep, nsweeps);
+  if (h->d.nranks > 1 && h->comm && h->p2p && nsweeps > 0 && h->tiled) {
+    if (h->dim == 3 && h->use_stream) return sweeps_p2p(h, first_sweep, nsweeps);
+    if (h->dim == 2 && h->use_fused && h->fused2d_ok && !getenv("SPK_CUDA_OVERLAP_2D"))
+      return sweeps_p2p_2d(h, first_sweep, nsweeps);
+  }
   const bool fused2d = h->tiled && h->use_fused && h->dim == 2 && h->fused2d_ok;
   // 3-D: 8 (2) exchanges per sweep, worth hiding.  2-D: one exchange of 4 rows per fused sweep; splitting
   // the single launch into boundary + interior launches costs more than the exchange it hides
@@ -930,11 +972,14 @@ int spk_cuda_energy(spk_cuda_handle *h, double *energy) {
 // the peer-memory halo.  The handles travel through one ncclAllGather; a second one makes every
 // rank agree on whether the mapping worked everywhere (otherwise all keep the NCCL exchange).
 static int setup_p2p(spk_cuda_handle *h) {
-  struct Ipc { cudaIpcMemHandle_t base, flags; int ok; int pad[3]; };
+  struct Ipc { cudaIpcMemHandle_t base, alt, flags; int ok; int pad[3]; };
   h->p2p = false;
   const char *np = getenv("SPK_CUDA_NO_P2P");
-  const int want = h->dim == 3 && h->stream_ok && h->nslab >= 2 && !(np && np[0] == '1');
+  const bool two = h->dim == 2;  // 2-D: both buffers of the out-of-place fused sweep
+  const int want = !(np && np[0] == '1') && h->nslab >= 2 &&
+                   (two ? (h->fused2d_ok && h->base_alt && h->nslab >= h->gh) : h->stream_ok);
   const int n = h->d.nranks, lower = (h->d.rank + n - 1) % n, upper = (h->d.rank + 1) % n;
+  int32_t *first = h->alloc0, *second = h->base == h->alloc0 ? h->base_alt : h->base;
   Ipc mine;
   memset(&mine, 0, sizeof mine);
   if (want) {
@@ -942,7 +987,8 @@ static int setup_p2p(spk_cuda_handle *h) {
       CU(cudaMalloc(&h->flags, 4 * sizeof(uint32_t)));
       CU(cudaMemset(h->flags, 0, 4 * sizeof(uint32_t)));
     }
-    mine.ok = cudaIpcGetMemHandle(&mine.base, h->base) == cudaSuccess &&
+    mine.ok = cudaIpcGetMemHandle(&mine.base, first) == cudaSuccess &&
+              (!two || cudaIpcGetMemHandle(&mine.alt, second) == cudaSuccess) &&
               cudaIpcGetMemHandle(&mine.flags, h->flags) == cudaSuccess;
     cudaGetLastError();
   }
@@ -964,11 +1010,14 @@ static int setup_p2p(spk_cuda_handle *h) {
     for (int side = 0; side < 2 && mine.ok; side++) {
       if (side == 1 && upper == lower) {
         h->peer_map[1] = h->peer_map[0];
+        h->peer_map_alt[1] = h->peer_map_alt[0];
         h->peer_flag_map[1] = h->peer_flag_map[0];
         continue;
       }
-      if (cudaIpcOpenMemHandle(&h->peer_map[side], all[peers[side]].base, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-          cudaIpcOpenMemHandle(&h->peer_flag_map[side], all[peers[side]].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      const Ipc &p = all[peers[side]];
+      if (cudaIpcOpenMemHandle(&h->peer_map[side], p.base, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          (two && cudaIpcOpenMemHandle(&h->peer_map_alt[side], p.alt, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ||
+          cudaIpcOpenMemHandle(&h->peer_flag_map[side], p.flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
         cudaGetLastError();
         mine.ok = 0;
       }
@@ -980,7 +1029,7 @@ static int setup_p2p(spk_cuda_handle *h) {
   cudaFree(dev);
   if (rc) return rc;
   if (every) {
-    // lower neighbour's UPPER ghost plane mirrors my plane 0; upper neighbour's LOWER ghost plane my last plane
+    // lower neighbour's UPPER ghost layer mirrors my first layer(s); upper neighbour's LOWER ghost layer my last
     h->mirror_lo = (int32_t *)h->peer_map[0] + (int64_t)(h->gh + h->nslab) * h->plane;
     h->mirror_hi = (int32_t *)h->peer_map[1];
     h->peer_flags[0] = (uint32_t *)h->peer_flag_map[0] + 1;  // I am the lower neighbour's upper neighbour
@@ -1025,7 +1074,8 @@ static int check_halo_timeout(spk_cuda_handle *h) {
 
 int spk_cuda_halo_mode(const spk_cuda_handle *h) {
   if (!h || h->d.nranks == 1) return 0;
-  return (h->p2p && h->tiled && h->use_stream) ? 2 : 1;
+  if (!h->p2p || !h->tiled) return 1;
+  return (h->dim == 3 ? h->use_stream : (h->use_fused && h->fused2d_ok)) ? 2 : 1;
 }
 
 int spk_cuda_sync(spk_cuda_handle *h) {

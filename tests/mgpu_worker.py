@@ -47,7 +47,8 @@ def main():
             idt = torch.frombuffer(bytearray(LatticeSweep.comm_id()), dtype=torch.uint8).cuda()
         dist.broadcast(idt, 0)
         s.comm_init(idt.cpu().numpy().tobytes())
-        want_mode = 2 if dim3 and os.environ.get("SPK_CUDA_NO_P2P") != "1" else 1
+        fused2d = not dim3 and (n[0] * nb) % 8 == 0  # the colour-fused 2-D kernel takes rows of 8-element multiples
+        want_mode = 2 if (dim3 or fused2d) and os.environ.get("SPK_CUDA_NO_P2P") != "1" else 1
         assert s.halo_mode() == want_mode, (model, lat, "halo mode", s.halo_mode())
         lo, hi = rank * s.nlocal, (rank + 1) * s.nlocal
         s.upload(spins[lo:hi])
