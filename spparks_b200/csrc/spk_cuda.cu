@@ -103,7 +103,10 @@ struct spk_cuda_handle {
   ncclComm_t comm = nullptr;
   bool tiled = true;  // tuned kernels allowed (SPK_CUDA_FORCE_GENERIC=1 disables, for A/B tests)
   bool use_stream = true;  // SPK_CUDA_NO_STREAM=1 keeps the strip kernel (A/B tests)
-  bool smem_attr_set[5] = {false, false, false, false, false};  // dynamic shared memory opt-in done: [0] tile2d, [1..4] stream variants
+  bool smem_attr_set[9] = {false, false, false, false, false, false, false, false, false};  // dynamic shared memory opt-in done: [0] tile2d, [1..8] stream variants
+  int32_t *edge = nullptr;     // tile-edge words of the colour-pair launches (StreamMap::edge)
+  size_t edge_words = 0;
+  bool use_pair = false;       // SPK_CUDA_PAIR=1: sc/26n colour pairs in one launch (half the DRAM traffic; measured slower)
   bool pk16 = false;       // every spin <= PK16_MAX_SPIN: packed 16-bit compares (SPK_CUDA_NO_PK16=1 disables, for A/B tests)
   bool stream_ok = false;  // TMA streaming kernel usable (3-D lattice, tensor map built)
   CUtensorMap tmap;        // (x, y, plane incl. the two ghost planes) view of the slab
@@ -356,16 +359,20 @@ int fused_sweep(spk_cuda_handle *h, int part) {
 }
 
 // returns 0 launched, -1 not applicable, >0 error
+// pair: colours c0 (even) and c0 + 1 of sc/26n in ONE launch (sweep_stream.cuh: stream_chunk_pair)
 template <int LAT, int MODEL>
-int launch_stream(spk_cuda_handle *h, const SweepArgs &a) {
+int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
   if constexpr (LAT != SPK_SC_26N && LAT != SPK_SC_6N) {
     return -1;
   } else {
+    if (pair && (LAT != SPK_SC_26N || MODEL == SPK_ISING || (a.c0 & 1) || a.nloop != 1)) return -1;
     using C = StreamCfg<LAT>;
     const Geo &g = a.g;
     const Box &b = a.b;
     if (!h->stream_ok || b.ilo != 0 || b.ihi != g.X || b.jlo != 0 || b.jhi != g.Y) return -1;
     StreamMap sm;
+    sm.edge = nullptr;
+    sm.nrows = 0;
     const int c0 = a.c0;
     int kfirst = b.klo, nq = b.khi - b.klo;
     if (LAT == SPK_SC_26N) {
@@ -387,10 +394,27 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a) {
     const int grid = sm.items < grid_max ? sm.items : grid_max;
     SweepArgs args = a;  // Geo::lo_wrap / hi_wrap select periodic images (1 GPU) or ghost planes (slabs)
     // P16: packed 16-bit compares (event.cuh) when every spin fits; the Ising shortcut has no compares to pack
-    auto launch = [&](auto ONE, auto PK) -> int {
+    auto launch = [&](auto ONE, auto PK, auto PAIR) -> int {
       constexpr bool one = decltype(ONE)::value, pk = decltype(PK)::value && MODEL != SPK_ISING;
-      auto *kern = sweep_stream_kernel<LAT, MODEL, one, pk>;
-      bool &attr = h->smem_attr_set[1 + (one ? 0 : 1) + (pk ? 2 : 0)];
+      constexpr bool pr = decltype(PAIR)::value && one && LAT == SPK_SC_26N && MODEL != SPK_ISING;
+      if constexpr (pr) {  // tile-edge words first (stream order: they see the lattice before the pair launch)
+        sm.nrows = g.Y / 2;
+        const size_t words = 2 * (size_t)sm.ntx * sm.nrows * sm.nq;
+        const size_t words_max = 2 * (size_t)sm.ntx * sm.nrows * ((h->nslab + 1) / 2);  // whole-slab launch: allocate once
+        if (words > h->edge_words) {
+          cudaFree(h->edge);
+          h->edge = nullptr;
+          h->edge_words = 0;
+          if (cudaMalloc(&h->edge, words_max * sizeof(int32_t)) != cudaSuccess) return 1;
+          h->edge_words = words_max;
+        }
+        sm.edge = h->edge;
+        const long long total = (long long)(words / 2);
+        edge_pair_kernel<MODEL, pk><<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(args, sm, h->edge);
+        h->launches++;
+      }
+      auto *kern = sweep_stream_kernel<LAT, MODEL, one, pk, pr>;
+      bool &attr = h->smem_attr_set[1 + (one ? 0 : 1) + (pk ? 2 : 0) + (pr ? 4 : 0)];
       if (!attr) {  // per handle: the attribute belongs to the device the handle lives on
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) return 1;
         attr = true;
@@ -400,8 +424,10 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a) {
     };
     using T = std::true_type;
     using F = std::false_type;
-    const int rc = args.nloop == 1 ? (h->pk16 ? launch(T{}, T{}) : launch(T{}, F{}))
-                                   : (h->pk16 ? launch(F{}, T{}) : launch(F{}, F{}));
+    int rc;
+    if (pair) rc = h->pk16 ? launch(T{}, T{}, T{}) : launch(T{}, F{}, T{});
+    else if (args.nloop == 1) rc = h->pk16 ? launch(T{}, T{}, F{}) : launch(T{}, F{}, F{});
+    else rc = h->pk16 ? launch(F{}, T{}, F{}) : launch(F{}, F{}, F{});
     if (rc) return rc;
     h->launches++;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
@@ -431,6 +457,36 @@ int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int
   }
   if (rng == RNG_INJECTED) return launch_generic<LAT, MODEL, RNG_INJECTED>(h, a);
   return launch_generic<LAT, MODEL, RNG_STRICT>(h, a);
+}
+
+// colours `color` (odd, 1-based) and color + 1 of sc/26n as one launch: 0 launched, -1 not applicable
+template <int MODEL> int sweep_pair_m(spk_cuda_handle *h, int color, const int32_t *box) {
+  SweepArgs a;
+  a.spin = h->spin; a.g = h->g; a.c0 = color - 1; a.nloop = 1; a.ev = h->ev;
+  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept;
+  a.mirror_lo = h->mirror_active ? h->mirror_lo : nullptr;
+  a.mirror_hi = h->mirror_active ? h->mirror_hi : nullptr;
+  if (!local_box(h, box, a.b)) return 0;
+  const int rc = launch_stream<SPK_SC_26N, MODEL>(h, a, true);
+  if (rc == 0) h->nattempt += class_count<SPK_SC_26N>(h, a.b, a.c0) + class_count<SPK_SC_26N>(h, a.b, a.c0 + 1);
+  return rc;
+}
+
+bool pair_ok(const spk_cuda_handle *h) {
+  return h->use_pair && h->tiled && h->use_stream && h->stream_ok && h->d.lattice == SPK_SC_26N && h->d.model != SPK_ISING;
+}
+
+int sweep_pair(spk_cuda_handle *h, int color, const int32_t *box) {
+  int rc = -1;
+  switch (h->d.model) {
+    case SPK_POTTS: rc = sweep_pair_m<SPK_POTTS>(h, color, box); break;
+    case SPK_POTTS_NEIGHONLY: rc = sweep_pair_m<SPK_POTTS_NEIGHONLY>(h, color, box); break;
+    case SPK_POTTS_PIN: rc = sweep_pair_m<SPK_POTTS_PIN>(h, color, box); break;
+    default: break;
+  }
+  if (rc > 0) return fail("colour-pair launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc < 0) return fail("colour-pair launch not applicable");
+  return 0;
 }
 
 template <int LAT> int sweep_set_l(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
@@ -539,6 +595,8 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
   h->use_stream = !(ns && ns[0] == '1');
   const char *nf = getenv("SPK_CUDA_NO_FUSED");
   h->use_fused = !(nf && nf[0] == '1');
+  const char *pairenv = getenv("SPK_CUDA_PAIR");
+  h->use_pair = pairenv && pairenv[0] == '1';
   const char *np = getenv("SPK_CUDA_NO_PK16");
   // spins are 1..Q (potts/pin: Q+1 marks a pinned site, src/app_potts_pin.cpp:81)
   h->pk16 = !(np && np[0] == '1') && desc->model != SPK_ISING &&
@@ -597,6 +655,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
     if (h->peer_flag_map[side]) cudaIpcCloseMemHandle(h->peer_flag_map[side]);
   }
   cudaFree(h->flags);
+  cudaFree(h->edge);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->base); cudaFree(h->base_alt); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
   if (h->t0) cudaEventDestroy(h->t0);
@@ -824,18 +883,21 @@ static int sweeps_p2p(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
   const int32_t hi_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0 + h->nslab - 1, h->g.g0 + h->nslab};
   const int32_t in_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0 + 1, h->g.g0 + h->nslab - 1};
   int rc = 0;
+  // sc/26n: a step is a colour PAIR (same z parity, so the same-step argument above holds unchanged)
+  const bool pair = pair_ok(h);
+  auto run = [&](int color, const int32_t *box) { return pair ? sweep_pair(h, color, box) : sweep_set(h, RNG_PHILOX, color, box, 1); };
   for (int s = 0; s < nsweeps && !rc; s++) {
     h->ev.sweep = first_sweep + (uint32_t)s;
-    for (int color = 1; color <= h->nc && !rc; color++) {
+    for (int color = 1; color <= h->nc && !rc; color += pair ? 2 : 1) {
       const uint32_t t = ++h->step;
       halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, t - 1);
       h->mirror_active = true;
-      rc = sweep_set(h, RNG_PHILOX, color, lo_box, 1);
-      if (!rc) rc = sweep_set(h, RNG_PHILOX, color, hi_box, 1);
+      rc = run(color, lo_box);
+      if (!rc) rc = run(color, hi_box);
       h->mirror_active = false;
       halo_signal_kernel<<<1, 32, 0, h->stream>>>(h->peer_flags[0], h->peer_flags[1], t);
       h->launches += 2;
-      if (!rc && h->nslab > 2) rc = sweep_set(h, RNG_PHILOX, color, in_box, 1);
+      if (!rc && h->nslab > 2) rc = run(color, in_box);
     }
   }
   // the neighbours' last stores into this rank's ghost planes must have landed before anything
@@ -923,6 +985,14 @@ int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
       rc = fused_sweep(h, 0);
       if (rc == 0) continue;
       if (rc > 0) return fail("fused sweep launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (h->d.nranks == 1 && pair_ok(h)) {  // sc/26n: two colours per launch (nothing to exchange on one GPU)
+      h->ghosts_valid = false;
+      for (int color = 1; color <= h->nc; color += 2) {
+        int rc = sweep_pair(h, color, nullptr);
+        if (rc) return rc;
+      }
+      continue;
     }
     for (int color = 1; color <= h->nc; color++) {
       int rc = spk_cuda_halo_exchange(h);

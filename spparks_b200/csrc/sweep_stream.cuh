@@ -37,6 +37,11 @@ template <int LAT> struct StreamCfg {
 struct StreamMap {
   int ntx, nty, nzc, items;  // tiles in x, y; plane chunks; ntx*nty*nzc
   int kfirst, nq, qchunk;    // first class plane (local index), class planes, class planes per item
+  // colour-pair launches (PAIR): per (class plane q, class row, x tile) two words made by
+  // edge_pair_kernel before the launch: [0] pre-launch spin of the odd-x site left of the tile,
+  // [1] post-colour-c0 spin of the tile's first even-x site
+  const int32_t *edge;
+  int nrows;                 // class rows of a plane (Y / 2)
 };
 
 // ---- mbarrier / TMA wrappers (PTX ISA: mbarrier, cp.async.bulk.tensor) ------------------------
@@ -184,7 +189,109 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
   return accepted;
 }
 
-template <int LAT, int MODEL, bool ONEPASS, bool P16>
+// Colour pair (c0, c0+1) of sc/26n in one pass over a class row: the two colours differ only in
+// the x parity, so the odd-x sites of a class row depend on the even-x sites of the SAME row and
+// on nothing else the launch changes (rows y+-1 and planes k+-1 belong to other colours).  A
+// thread updates the even sites of its chunk (elements 0, 2), takes the next lane's new element 0
+// by shuffle, then updates the odd sites (1, 3) and stores the chunk once.  Across the tile edge
+// the two values a tile cannot know come from edge_pair_kernel (StreamMap::edge): the pre-launch
+// spin left of the tile (the neighbouring tile may already have rewritten it in memory) and the
+// post-c0 spin of the next tile's first site.  A launch then reads the lattice once for two
+// colours: 20 instead of 36 bytes per site-update and sweep.
+template <int LAT, int MODEL, bool P16>
+__device__ __forceinline__ int stream_chunk_pair(const SweepArgs &a, const int32_t *const (&pl)[3], int r, int lane,
+                                                 bool valid, int32_t *gchunk, int32_t *gmirror,
+                                                 unsigned long long gsite0, bool use_left, int left_pre,
+                                                 bool use_right, int right_new) {
+  using L = Lat<LAT>;
+  constexpr int NN = L::NN;
+  using R = RowInfo<LAT, 0>;
+  int W[9][6];  // W[row][1 + e] = element e of the chunk, e in [-1, 4]
+  static_for<9>([&](auto RR) {
+    constexpr int rr = decltype(RR)::value, dy = rr % 3 - 1, dz = rr / 3 - 1;
+    if constexpr (R::used(dy, dz)) {
+      const int32_t *rowp = pl[dz + 1] + (r + dy) * ST_BX + 4 + 4 * lane;
+      const int4 t = *reinterpret_cast<const int4 *>(rowp);
+      W[rr][1] = t.x; W[rr][2] = t.y; W[rr][3] = t.z; W[rr][4] = t.w;
+      W[rr][0] = rowp[-1];
+      W[rr][5] = rowp[4];
+    }
+  });
+  if (use_left) W[4][0] = left_pre;
+  const int before[4] = {W[4][1], W[4][2], W[4][3], W[4][4]};
+  int accepted = 0;
+  static_for<2>([&](auto PP) {
+    constexpr int P = decltype(PP)::value;  // 0: colour c0 (even x), 1: colour c0 + 1 (odd x)
+    if constexpr (P == 1) {
+      const int nxt = __shfl_down_sync(0xffffffffu, W[4][1], 1);  // next lane's updated element 0
+      W[4][5] = use_right ? right_new : nxt;
+    }
+    const unsigned long long leader = gsite0 + P;
+    const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep,
+                                    (uint32_t)(a.c0 + P + 1), a.ev.rk);
+    int nw[2];
+    static_for<2>([&](auto H) {
+      constexpr int h = decltype(H)::value, e = P + 2 * h;
+      int v[NN];
+      static_for<NN>([&](auto N_) {
+        constexpr int n = decltype(N_)::value;
+        constexpr Off o = L::off(0, n);
+        v[n] = W[(o.dz + 1) * 3 + (o.dy + 1)][1 + e + o.dx];
+      });
+      Draws<RNG_PHILOX> d;
+      d.w1 = h ? blk.z : blk.x;
+      d.w2 = h ? blk.w : blk.y;
+      nw[h] = site_event<MODEL, RNG_PHILOX, NN, P16>(a.ev, W[4][1 + e], v, d);
+      accepted += (nw[h] != W[4][1 + e]);
+    });
+    // the two sites of one colour are not neighbours: write both after both were evaluated
+    W[4][1 + P] = nw[0];
+    W[4][3 + P] = nw[1];
+  });
+  if (!valid) return 0;
+  if (W[4][1] != before[0] || W[4][2] != before[1] || W[4][3] != before[2] || W[4][4] != before[3]) {
+    const int4 nv = make_int4(W[4][1], W[4][2], W[4][3], W[4][4]);
+    *reinterpret_cast<int4 *>(gchunk) = nv;
+    if (gmirror) *reinterpret_cast<int4 *>(gmirror) = nv;
+  }
+  return accepted;
+}
+
+// The values a colour-pair launch needs across its tile edges (see stream_chunk_pair), one thread
+// per (x tile, class row, class plane): the site at the tile's first column is evaluated for
+// colour c0 exactly as the tile's own lane 0 will evaluate it (same neighbours, same Philox
+// words) but stored here instead of into the lattice, next to the current spin left of it.
+template <int MODEL, bool P16>
+__global__ void __launch_bounds__(256) edge_pair_kernel(const __grid_constant__ SweepArgs a,
+                                                        const __grid_constant__ StreamMap sm, int32_t *edge) {
+  using L = Lat<SPK_SC_26N>;
+  constexpr int NN = L::NN;
+  const Geo &g = a.g;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)sm.ntx * sm.nrows * sm.nq) return;
+  const int b = (int)(idx % sm.ntx), rc = (int)((idx / sm.ntx) % sm.nrows), q = (int)(idx / ((long long)sm.ntx * sm.nrows));
+  const int i = b * ST_TX, j = 2 * rc + ((a.c0 >> 1) & 1), k = sm.kfirst + 2 * q;
+  const int xi[3] = {i == 0 ? g.X - 1 : i - 1, i, i == g.X - 1 ? 0 : i + 1};
+  const int yj[3] = {j == 0 ? g.Y - 1 : j - 1, j, j == g.Y - 1 ? 0 : j + 1};
+  const int zk[3] = {k == 0 ? g.lo_wrap : k - 1, k, k == g.Z - 1 ? g.hi_wrap : k + 1};
+  const long long sy = g.X, sz = sy * g.Y;
+  int v[NN];
+#pragma unroll
+  for (int n = 0; n < NN; n++) {
+    const Off o = L::off(0, n);
+    v[n] = a.spin[zk[o.dz + 1] * sz + yj[o.dy + 1] * sy + xi[o.dx + 1]];
+  }
+  const int cur = a.spin[zk[1] * sz + yj[1] * sy + i];
+  const unsigned long long gsite = ((unsigned long long)(k + g.g0) * g.gY + j) * (unsigned long long)g.gX + i;
+  const uint4 blk = philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32), a.ev.sweep, (uint32_t)(a.c0 + 1), a.ev.rk);
+  Draws<RNG_PHILOX> d;
+  d.w1 = blk.x;  // i is a multiple of 4: the site leads its Philox block (event.cuh: philox_words)
+  d.w2 = blk.y;
+  edge[2 * idx] = v[4];  // (dx,dy,dz) = (-1,0,0): neighbour 4 in reference order
+  edge[2 * idx + 1] = site_event<MODEL, RNG_PHILOX, NN, P16>(a.ev, cur, v, d);
+}
+
+template <int LAT, int MODEL, bool ONEPASS, bool P16, bool PAIR = false>
 #ifndef ST_MINB
 #define ST_MINB 2
 #endif
@@ -279,7 +386,25 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           y = y0 + cr;
           px = (a.c0 + y + k + g.g0) & 1;
         }
-        if (y < Y && x < rowlen) {  // y: warp-uniform
+        if constexpr (PAIR) {
+          if (y < Y) {  // warp-uniform; lanes past the row end run along (shuffle) without storing
+            const int r = y - y0 + 1;
+            const bool valid = x < rowlen;
+            int32_t *gchunk = a.spin + (long long)k * sz + (long long)y * sy + x;
+            int32_t *gmirror = nullptr;
+            if (k == 0 && a.mirror_lo) gmirror = a.mirror_lo + (long long)y * sy + x;
+            if (k == g.Z - 1 && a.mirror_hi) gmirror = a.mirror_hi + (long long)y * sy + x;
+            const unsigned long long gsite0 =
+                ((unsigned long long)(k + g.g0) * g.gY + y) * (unsigned long long)g.gX + x;
+            const long long ebase = ((long long)(q0 + s) * sm.nrows + (y >> 1)) * sm.ntx;
+            const bool use_left = lane == 0, use_right = valid && (lane == 31 || x + 4 >= rowlen);
+            int left_pre = 0, right_new = 0;
+            if (use_left) left_pre = sm.edge[2 * (ebase + tx)];
+            if (use_right) right_new = sm.edge[2 * (ebase + (x + 4 >= rowlen ? 0 : tx + 1)) + 1];
+            accepted += stream_chunk_pair<LAT, MODEL, P16>(a, pl, r, lane, valid, gchunk, gmirror, gsite0, use_left,
+                                                           left_pre, use_right, right_new);
+          }
+        } else if (y < Y && x < rowlen) {  // y: warp-uniform
           const int r = y - y0 + 1;
           int32_t *gchunk = a.spin + (long long)k * sz + (long long)y * sy + x;
           int32_t *gmirror = nullptr;  // k: CTA-uniform

@@ -122,15 +122,17 @@ CASES = [
 
 
 @pytest.mark.parametrize("model,lat,n,q,T", CASES, ids=lambda v: str(v).replace(" ", ""))
-@pytest.mark.parametrize("kernel", ["tuned", "tuned32", "strip", "generic"])
+@pytest.mark.parametrize("kernel", ["tuned", "tuned32", "pair", "strip", "generic"])
 def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, kernel, monkeypatch):
     """Production (Philox) mode, three full sweeps, through every kernel family (TMA streaming
-    kernel where it applies — with packed 16-bit and with 32-bit compares —, strip kernel, generic
-    kernel): bit-exact against the oracle evaluating the same counter-based stream."""
+    kernel where it applies — colour-pair launches, per-colour launches, packed 16-bit and 32-bit
+    compares —, strip kernel, generic kernel): bit-exact against the oracle evaluating the same counter-based stream."""
     if kernel == "generic":
         monkeypatch.setenv("SPK_CUDA_FORCE_GENERIC", "1")
     if kernel == "tuned32":
         monkeypatch.setenv("SPK_CUDA_NO_PK16", "1")
+    if kernel == "pair":  # sc/26n: one launch per colour PAIR (opt-in) instead of one per colour
+        monkeypatch.setenv("SPK_CUDA_PAIR", "1")
     if kernel == "strip":
         monkeypatch.setenv("SPK_CUDA_NO_STREAM", "1")
         monkeypatch.setenv("SPK_CUDA_NO_FUSED", "1")
