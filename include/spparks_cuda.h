@@ -110,6 +110,18 @@ int spk_cuda_reset_counters(spk_cuda_handle *h);
 /* diag_style energy (src/diag_energy.cpp:53-66): sum of site_energy over owned sites */
 int spk_cuda_energy(spk_cuda_handle *h, double *energy);
 
+/* diag_style cluster (src/diag_cluster.cpp:230-366, 585-612; AppLattice::push_connected_neighbors,
+ * src/app_lattice.cpp:1187-1201): connected components of equal-spin sites over the lattice's
+ * neighbour stencil, computed on the device.  ncluster, mean_volume (<N>) and mean_radius (<R> =
+ * mean of volume^(1/dimension)) are the three columns DiagCluster::stats prints
+ * (src/diag_cluster.cpp:894-897).  Single-GPU handles (nranks == 1) with fewer than 2^32 sites. */
+int spk_cuda_cluster_stats(spk_cuda_handle *h, int64_t *ncluster, double *mean_volume, double *mean_radius);
+/* the per-site cluster ids (1-based, the reference's numbering: clusters in the order of their
+ * lowest site index, as the scan of analyze_clusters opens them) and the volume of every cluster
+ * in that order; ids has room for nlocal entries, volumes for nvolumes entries (>= ncluster);
+ * either pointer may be NULL.  Runs the analysis itself. */
+int spk_cuda_cluster_ids(spk_cuda_handle *h, int32_t *ids, int64_t *volumes, int64_t nvolumes);
+
 /* multi-GPU: one process per GPU; rank 0 creates the id, the host broadcasts it (MPI_Bcast in
  * the plugin, torch.distributed in bench.py), every rank joins.  Replaces CommLattice::init
  * (src/comm_lattice.cpp:74-135). */

@@ -85,6 +85,8 @@ def lib():
         L.orc_accept_threshold.argtypes = [C.c_double, C.c_int]
         L.orc_run_sweep_random.argtypes = [C.c_void_p, i32p, C.POINTER(Mars), C.c_int, C.c_double,
                                            C.c_double, C.POINTER(StatsRow), C.c_int]
+        L.orc_clusters.restype = C.c_int64
+        L.orc_clusters.argtypes = [C.c_void_p, i32p, i32p, i64p, dp, dp]
         L.orc_nbasis.argtypes = [C.c_int]
         L.orc_maxneigh.argtypes = [C.c_int]
         L.orc_ncolors.argtypes = [C.c_int]
@@ -155,6 +157,16 @@ class Oracle:
 
     def total_energy(self, spin):
         return self.L.orc_total_energy(self.ctx, _i32(spin))
+
+    def clusters(self, spin):
+        """diag_style cluster: (ncluster, <N>, <R>, cluster_ids[nsites] (1-based, reference numbering),
+        volumes[ncluster])."""
+        ids = np.zeros(self.nsites, dtype=np.int32)
+        vol = np.zeros(self.nsites, dtype=np.int64)
+        mv, mr = C.c_double(), C.c_double()
+        n = int(self.L.orc_clusters(self.ctx, _i32(spin), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                    vol.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(mv), C.byref(mr)))
+        return n, mv.value, mr.value, ids, vol[:n].copy()
 
     def halfsweep_injected(self, spin, color, u1, u2, box=None):
         return self.L.orc_halfsweep_injected(self.ctx, _i32(spin), color, _box(box), _f64(u1), _f64(u2))

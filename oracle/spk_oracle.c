@@ -261,6 +261,50 @@ double orc_total_energy(const orc_ctx *c, const int32_t *spin) { /* src/diag_ene
   return e;
 }
 
+/* DiagCluster::analyze_clusters (src/diag_cluster.cpp:286-354): sites in increasing local index;
+ * an unvisited site opens cluster ncluster+1 (AppLattice::push_new_site, src/app_lattice.cpp:1170-1178)
+ * and a stack flood fill marks every equal-spin neighbour (push_connected_neighbors,
+ * src/app_lattice.cpp:1187-1201).  Serial, fully periodic: no ghost merging pass. */
+int64_t orc_clusters(const orc_ctx *c, const int32_t *spin, int32_t *cluster_ids, int64_t *volumes,
+                     double *mean_volume, double *mean_radius) {
+  const int64_t n = orc_nsites(c);
+  const int nn = c->maxneigh;
+  int64_t *stack = (int64_t *)malloc((size_t)n * sizeof(int64_t));
+  int64_t nb[ORC_MAXNEIGH];
+  int64_t ncluster = 0;
+  memset(cluster_ids, 0, (size_t)n * sizeof(int32_t));
+  for (int64_t i = 0; i < n; i++) {
+    if (cluster_ids[i] != 0) continue;
+    const int32_t id = (int32_t)(ncluster + 1);
+    int64_t top = 0, vol = 0;
+    stack[top++] = i;
+    cluster_ids[i] = id;
+    ncluster++;
+    while (top) {
+      const int64_t ii = stack[--top];
+      vol++;
+      orc_neighbors(c, ii, nb);
+      for (int j = 0; j < nn; j++)
+        if (spin[nb[j]] == spin[ii] && cluster_ids[nb[j]] == 0) {
+          stack[top++] = nb[j];
+          cluster_ids[nb[j]] = id;
+        }
+    }
+    volumes[ncluster - 1] = vol;
+  }
+  free(stack);
+  /* stats (src/diag_cluster.cpp:595-605) */
+  double volsum = 0.0, rsum = 0.0;
+  const double invdim = 1.0 / c->dim;
+  for (int64_t k = 0; k < ncluster; k++) {
+    volsum += (double)volumes[k];
+    rsum += pow((double)volumes[k], invdim);
+  }
+  if (mean_volume) *mean_volume = volsum / (double)ncluster;
+  if (mean_radius) *mean_radius = rsum / (double)ncluster;
+  return ncluster;
+}
+
 static int count_unlike(const int32_t *spin, const int64_t *nb, int nn, int value) {
   int e = 0;
   for (int n = 0; n < nn; n++) e += value != spin[nb[n]];

@@ -23,7 +23,8 @@ SYMBOLS = [
     "spk_cuda_set_siteseeds", "spk_cuda_get_siteseeds", "spk_cuda_sweep_color_strict", "spk_cuda_sweeps",
     "spk_cuda_counters", "spk_cuda_reset_counters", "spk_cuda_energy", "spk_cuda_comm_id",
     "spk_cuda_comm_init", "spk_cuda_halo_exchange", "spk_cuda_halo_mode", "spk_cuda_sync", "spk_cuda_timer_start",
-    "spk_cuda_timer_stop", "spk_cuda_launch_count", "spk_cuda_device_spins",
+    "spk_cuda_timer_stop", "spk_cuda_launch_count", "spk_cuda_device_spins", "spk_cuda_cluster_stats",
+    "spk_cuda_cluster_ids",
 ]
 
 
@@ -77,6 +78,8 @@ def load():
     L.spk_cuda_comm_init.argtypes = [vp, C.c_char_p]
     L.spk_cuda_halo_exchange.argtypes = [vp]
     L.spk_cuda_halo_mode.argtypes = [vp]
+    L.spk_cuda_cluster_stats.argtypes = [vp, i64p, dp, dp]
+    L.spk_cuda_cluster_ids.argtypes = [vp, i32p, i64p, C.c_int64]
     L.spk_cuda_sync.argtypes = [vp]
     L.spk_cuda_timer_start.argtypes = [vp]
     L.spk_cuda_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]

@@ -15,6 +15,7 @@
 
 #include "../../include/spparks_cuda.h"
 #include "aux_kernels.cuh"
+#include "cluster.cuh"
 #include "sweep_generic.cuh"
 #include "sweep_stream.cuh"
 #include "sweep_tile2d.cuh"
@@ -104,6 +105,9 @@ struct spk_cuda_handle {
   bool tiled = true;  // tuned kernels allowed (SPK_CUDA_FORCE_GENERIC=1 disables, for A/B tests)
   bool use_stream = true;  // SPK_CUDA_NO_STREAM=1 keeps the strip kernel (A/B tests)
   bool smem_attr_set[9] = {false, false, false, false, false, false, false, false, false};  // dynamic shared memory opt-in done: [0] tile2d, [1..8] stream variants
+  uint32_t *cl_label = nullptr, *cl_size = nullptr;  // diag_style cluster: union-find parents, volumes / ids per root
+  uint32_t *cl_blocksum = nullptr;
+  unsigned long long *cl_count = nullptr;             // [0] ncluster, [1] (as double) sum of radii
   int32_t *edge = nullptr;     // tile-edge words of the colour-pair launches (StreamMap::edge)
   size_t edge_words = 0;
   bool use_pair = false;       // SPK_CUDA_PAIR=1: sc/26n colour pairs in one launch (half the DRAM traffic; measured slower)
@@ -656,6 +660,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   }
   cudaFree(h->flags);
   cudaFree(h->edge);
+  cudaFree(h->cl_label); cudaFree(h->cl_size); cudaFree(h->cl_blocksum); cudaFree(h->cl_count);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->base); cudaFree(h->base_alt); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
   if (h->t0) cudaEventDestroy(h->t0);
@@ -1139,6 +1144,89 @@ static int check_halo_timeout(spk_cuda_handle *h) {
   CU(cudaMemcpyAsync(&timed_out, h->flags + 2, sizeof timed_out, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   if (timed_out) return fail("peer-memory halo: a neighbour rank did not signal its boundary step within 20 s");
+  return 0;
+}
+
+// union-find over the current lattice: labels flattened to roots, volumes per root, ncluster and
+// the radius sum on the device; returns ncluster and the radius sum
+static int cluster_analyse(spk_cuda_handle *h, unsigned long long *ncluster, double *rsum) {
+  if (h->d.nranks != 1) return fail("cluster analysis across slabs is not implemented (nranks must be 1)");
+  if (h->nlocal >= (int64_t)1 << 32) return fail("cluster analysis needs fewer than 2^32 sites");
+  CU(cudaSetDevice(h->d.device));
+  const long long n = h->nlocal;
+  if (!h->cl_label) {
+    CU(cudaMalloc(&h->cl_label, (size_t)n * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->cl_size, (size_t)n * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->cl_blocksum, (size_t)((n + CL_TILE - 1) / CL_TILE) * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->cl_count, 2 * sizeof(unsigned long long)));
+  }
+  const int grid = 148 * 16;
+  cluster_init_kernel<<<grid, 256, 0, h->stream>>>(h->cl_label, h->cl_size, n);
+  const int X = h->g.gX, Y = h->g.gY, Z = h->dim == 3 ? h->g.gZ : 1;
+  switch (h->d.lattice) {
+    case SPK_SQ_4N: launch_cluster_link<SPK_SQ_4N>(h->stream, h->spin, h->cl_label, X, Y, Z); break;
+    case SPK_SQ_8N: launch_cluster_link<SPK_SQ_8N>(h->stream, h->spin, h->cl_label, X, Y, Z); break;
+    case SPK_TRI: launch_cluster_link<SPK_TRI>(h->stream, h->spin, h->cl_label, X, Y, Z); break;
+    case SPK_SC_6N: launch_cluster_link<SPK_SC_6N>(h->stream, h->spin, h->cl_label, X, Y, Z); break;
+    case SPK_SC_26N: launch_cluster_link<SPK_SC_26N>(h->stream, h->spin, h->cl_label, X, Y, Z); break;
+    default: return fail("unknown lattice %d", h->d.lattice);
+  }
+  cluster_flatten_kernel<<<grid, 256, 0, h->stream>>>(h->cl_label, h->cl_size, n);
+  CU(cudaMemsetAsync(h->cl_count, 0, 2 * sizeof(unsigned long long), h->stream));
+  cluster_stats_kernel<<<grid, 256, 0, h->stream>>>(h->cl_label, h->cl_size, n, 1.0 / h->dim, h->cl_count,
+                                                    reinterpret_cast<double *>(h->cl_count + 1));
+  h->launches += 4;
+  CU(cudaGetLastError());
+  unsigned long long out[2];
+  CU(cudaMemcpyAsync(out, h->cl_count, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *ncluster = out[0];
+  memcpy(rsum, &out[1], sizeof(double));
+  return 0;
+}
+
+int spk_cuda_cluster_stats(spk_cuda_handle *h, int64_t *ncluster, double *mean_volume, double *mean_radius) {
+  if (!h) return fail("null handle");
+  unsigned long long nc = 0;
+  double rsum = 0.0;
+  const int rc = cluster_analyse(h, &nc, &rsum);
+  if (rc) return rc;
+  if (ncluster) *ncluster = (int64_t)nc;
+  // volsum = every site is in exactly one cluster (src/diag_cluster.cpp:595-605)
+  if (mean_volume) *mean_volume = (double)h->nlocal / (double)nc;
+  if (mean_radius) *mean_radius = rsum / (double)nc;
+  return 0;
+}
+
+int spk_cuda_cluster_ids(spk_cuda_handle *h, int32_t *ids, int64_t *volumes, int64_t nvolumes) {
+  if (!h) return fail("null handle");
+  unsigned long long nc = 0;
+  double rsum = 0.0;
+  int rc = cluster_analyse(h, &nc, &rsum);
+  if (rc) return rc;
+  if (volumes && nvolumes < (int64_t)nc) return fail("volumes has room for %lld clusters, %llu found", (long long)nvolumes, nc);
+  const long long n = h->nlocal;
+  const int nb = (int)((n + CL_TILE - 1) / CL_TILE);
+  long long *dvol = nullptr;
+  CU(cudaMalloc(&dvol, (size_t)nc * sizeof(long long)));
+  cluster_scan_blocksums<<<nb, 256, 0, h->stream>>>(h->cl_label, n, h->cl_blocksum);
+  cluster_scan_offsets<<<1, 1024, 0, h->stream>>>(h->cl_blocksum, nb);
+  cluster_scan_apply<<<nb, 256, 0, h->stream>>>(h->cl_label, h->cl_size, n, h->cl_blocksum, dvol);
+  h->launches += 3;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && volumes)
+    e = cudaMemcpyAsync(volumes, dvol, (size_t)nc * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && ids) {
+    // the parent array is not needed any more once every site knows its root's id: reuse it
+    cluster_ids_kernel<<<148 * 16, 256, 0, h->stream>>>(h->cl_label, h->cl_size, n, reinterpret_cast<int32_t *>(h->cl_label));
+    h->launches++;
+    e = cudaGetLastError();
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(ids, h->cl_label, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(dvol);
+  if (e != cudaSuccess) return fail("cluster ids: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -118,6 +118,21 @@ class LatticeSweep:
         _lib.check(self.L.spk_cuda_energy(self.h, C.byref(e)))
         return e.value
 
+    def cluster_stats(self):
+        """diag_style cluster on the device: (Nclust, <N>, <R>) of the reference's stats line."""
+        n, mv, mr = C.c_int64(), C.c_double(), C.c_double()
+        _lib.check(self.L.spk_cuda_cluster_stats(self.h, C.byref(n), C.byref(mv), C.byref(mr)))
+        return int(n.value), mv.value, mr.value
+
+    def cluster_ids(self):
+        """(ids[nlocal] int32 in the reference's numbering, volumes[ncluster] int64)."""
+        nc = self.cluster_stats()[0]
+        ids = np.empty(self.nlocal, dtype=np.int32)
+        vol = np.empty(nc, dtype=np.int64)
+        _lib.check(self.L.spk_cuda_cluster_ids(self.h, ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               vol.ctypes.data_as(C.POINTER(C.c_int64)), nc))
+        return ids, vol
+
     # -- multi-GPU -----------------------------------------------------------------------------
     @staticmethod
     def comm_id():
