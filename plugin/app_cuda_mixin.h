@@ -34,11 +34,12 @@
 #include "error.h"
 
 #include "spparks_cuda.h"
+#include "spk_cuda_host.h"
 
 namespace SPPARKS_NS {
 
 template <class Base, int MODEL>
-class AppCudaMixin : public Base {
+class AppCudaMixin : public Base, public SpkCudaHost {
  public:
   AppCudaMixin(class SPPARKS *spk, int narg, char **arg) : Base(spk,narg,arg)
   {
@@ -62,6 +63,7 @@ class AppCudaMixin : public Base {
     seed = 0;
     sweep_counter = 0;
     warned = 0;
+    device_current = 0;
   }
 
   virtual ~AppCudaMixin() { if (handle) spk_cuda_destroy(handle); }
@@ -127,6 +129,7 @@ class AppCudaMixin : public Base {
     desc.rank = this->me;
     desc.nranks = this->nprocs;
     check(spk_cuda_create(&desc,&handle));
+    device_current = 0;      // the host copy (create_sites, set, pin, a previous run) is the only one
     if (spk_cuda_nlocal(handle) != this->nlocal)
       this->error->one(FLERR,"app_style */cuda: slab size does not match nlocal");
 
@@ -158,6 +161,7 @@ class AppCudaMixin : public Base {
 
     check(spk_cuda_set_temperature(handle,this->temperature));
     check(spk_cuda_upload_spins(handle,this->iarray[0],this->nlocal));
+    device_current = 1;      // from here on the device is ahead or (after every download) equal
     if (strict) check(spk_cuda_set_siteseeds(handle,this->siteseeds,this->nlocal));
     check(spk_cuda_reset_counters(handle));
     bigint naccept0 = this->naccept;
@@ -213,9 +217,23 @@ class AppCudaMixin : public Base {
     if (strict) check(spk_cuda_get_siteseeds(handle,this->siteseeds,this->nlocal));
   }
 
+  // SpkCudaHost: the /cuda diagnostics read the device lattice.  Output::compute is only ever
+  // called when host and device agree (after the download above) or before the first sweep of a
+  // run (Output::setup), when only the host copy exists.
+
+  spk_cuda_handle *cuda_lattice()
+  {
+    if (!handle) this->error->one(FLERR,"app_style */cuda: no device lattice before init");
+    if (!device_current) {
+      check(spk_cuda_upload_spins(handle,this->iarray[0],this->nlocal));
+      device_current = 1;
+    }
+    return handle;
+  }
+
  private:
   spk_cuda_handle *handle;
-  int device,nspins_cuda,seed_set,warned;
+  int device,nspins_cuda,seed_set,warned,device_current;
   uint64_t seed;
   uint32_t sweep_counter;
 

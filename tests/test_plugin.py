@@ -162,3 +162,42 @@ run %.17g
         nacc += o.sweep_philox(want, 987654321, sw)
         assert int(rows[sw + 1][1]) == s.counters()[0] == nacc
         assert float(rows[sw + 1][4]) == s.energy() == o.total_energy(want)
+
+
+@pytest.mark.parametrize("app,q,dim,lat,n,T", [
+    ("potts/neighonly", 60, 3, "sc/26n", (24, 16, 20), 0.5),
+    ("potts", 12, 2, "tri", (48, 30, 1), 0.4),
+    ("ising", 2, 2, "sq/4n", (64, 48, 1), 0.9),
+], ids=["neighonly-sc26n", "potts-tri", "ising-sq4n"])
+def test_device_diagnostics_equal_host_diagnostics(app, q, dim, lat, n, T):
+    """`diag_style energy/cuda` and `diag_style cluster/cuda` (plugin/diag_*_cuda.h: the sums and
+    the connected-component analysis on the device) next to the reference's own host-side
+    `diag_style energy` and `diag_style cluster` in the same run: identical stats columns at every
+    output, including the one at time 0 that precedes the first sweep."""
+    style = app + "/cuda" if app == "ising" else "%s/cuda %d" % (app, q)
+    dt = 0.5 if app == "ising" else (1.0 / 26 if app == "potts/neighonly" else 1.0 / q)
+    zr = "0 %d" % n[2] if dim == 3 else "-0.5 0.5"
+    script = """seed 777
+app_style %s
+dimension %d
+lattice %s 1.0
+region box block 0 %d 0 %d %s
+create_box box
+create_sites box
+set site range 1 %d
+sweep color
+sector no
+temperature %r
+diag_style energy
+diag_style cluster
+diag_style energy/cuda
+diag_style cluster/cuda
+stats %.17g
+run %.17g
+""" % (style, dim, lat, n[0], n[1], zr, q, T, dt * 3.999, dt * 20.5)
+    rows = stats_rows(run(SPK_CUDA, script))
+    assert len(rows) >= 6
+    for r in rows:
+        host, dev = r[4:8], r[8:12]   # Energy Nclust <N> <R> | the same four from the device
+        assert host == dev, r
+    assert int(rows[-1][5]) < int(rows[0][5])  # the lattice coarsens
