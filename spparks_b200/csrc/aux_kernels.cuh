@@ -27,6 +27,19 @@ __global__ void pin_kernel(int32_t *spin, long long n, long long goff, unsigned 
   }
 }
 
+// init_app's spin check (src/app_potts.cpp:83-90, src/app_ising.cpp:74-81, src/app_potts_pin.cpp:78-84):
+// number of sites whose value lies outside [lo, hi]
+__global__ void __launch_bounds__(256) validate_kernel(const int32_t *__restrict__ spin, long long n, int lo, int hi,
+                                                       unsigned long long *bad) {
+  unsigned int c = 0;
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n; s += (long long)gridDim.x * blockDim.x) {
+    const int v = spin[s];
+    c += (v < lo || v > hi);
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(bad, (unsigned long long)c);
+}
+
 // diag_style energy (src/diag_energy.cpp:53-66): sum over owned sites of site_energy(i)
 template <int LAT>
 __global__ void __launch_bounds__(256) energy_kernel(const int32_t *__restrict__ spin, Geo g, unsigned long long *out) {

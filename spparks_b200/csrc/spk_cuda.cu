@@ -681,8 +681,17 @@ int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n) {
   if (n != h->nlocal) return fail("upload of %lld sites, slab owns %lld", (long long)n, (long long)h->nlocal);
   CU(cudaSetDevice(h->d.device));
   CU(cudaMemcpyAsync(h->spin, host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
   h->ghosts_valid = false;
+  // the reference's init_app refuses spins outside 1..Q (Q+1 = pinned for potts/pin); the kernels
+  // rely on it (packed 16-bit compares), so the check is repeated where the spins enter the device
+  const int hi = h->d.model == SPK_ISING ? 2 : h->d.nspins + (h->d.model == SPK_POTTS_PIN ? 1 : 0);
+  CU(cudaMemsetAsync(h->escratch, 0, sizeof(unsigned long long), h->stream));
+  validate_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, n, 1, hi, h->escratch);
+  h->launches++;
+  unsigned long long bad = 0;
+  CU(cudaMemcpyAsync(&bad, h->escratch, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (bad) return fail("One or more sites have invalid values (%llu of %lld outside 1..%d)", bad, (long long)n, hi);
   return 0;
 }
 

@@ -232,6 +232,17 @@ def test_edge_sizes_and_errors():
         s.sweep_color(0, 9)
     with pytest.raises(SpkCudaError, match="slab owns"):
         s.upload(np.zeros(10, dtype=np.int32))
+    # init_app's spin check (src/app_potts.cpp:83-90): values outside 1..Q are refused on upload
+    bad = np.ones(512, dtype=np.int32)
+    bad[100] = 6
+    with pytest.raises(SpkCudaError, match="invalid values"):
+        s.upload(bad)
+    bad[100] = 0
+    with pytest.raises(SpkCudaError, match="invalid values"):
+        s.upload(bad)
+    p = LatticeSweep("potts/pin", "sc/26n", 8, 8, 8, nspins=5)
+    bad[100] = 6  # Q+1 marks a pinned site (src/app_potts_pin.cpp:81)
+    p.upload(bad)
 
 
 def test_device_randomize_distribution():
