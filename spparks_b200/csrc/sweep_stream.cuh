@@ -349,8 +349,25 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       __syncthreads();
     }
 
+    // the two class rows of this warp: everything that does not depend on the plane is computed
+    // once per item; the plane-dependent parts are running values advanced per step
+    const int x = x0 + 4 * lane;
+    int yrow[2];
+    long long rowoff[2];            // element offset of the thread's chunk inside a plane
+    unsigned long long rowsite[2];  // its global site index inside a plane
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const int cr = warp + 8 * t;
+      yrow[t] = LAT == SPK_SC_26N ? y0 + 2 * cr + ((a.c0 >> 1) & 1) : y0 + cr;
+      rowoff[t] = (long long)yrow[t] * sy + x;
+      rowsite[t] = (unsigned long long)yrow[t] * (unsigned long long)g.gX + x;
+    }
+    int32_t *kbase = a.spin + (long long)kstart * sz;  // plane k of the lattice
+    unsigned long long ksite = (unsigned long long)(kstart + g.g0) * g.gY * (unsigned long long)g.gX;
+    const bool mirrors = a.mirror_lo != nullptr || a.mirror_hi != nullptr;  // boundary launches of a slab run only
+
     int pv[C::KSTEP][2];  // patch values of the planes in flight
-    for (int s = 0; s < nsteps; s++) {
+    for (int s = 0; s < nsteps; s++, kbase += C::KSTEP * sz, ksite += (unsigned long long)C::KSTEP * g.gY * g.gX) {
       const int k = kstart + s * C::KSTEP;
       const uint32_t Qs = Q + s * C::KSTEP;  // sequence number of plane k-1
 
@@ -374,28 +391,22 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       }
 
       const int32_t *const pl[3] = {plane_ptr(Qs), plane_ptr(Qs + 1), plane_ptr(Qs + 2)};
-      const int x = x0 + 4 * lane;
+      int32_t *mbase = nullptr;  // ghost plane of the ring neighbour that mirrors plane k (CTA-uniform)
+      if (mirrors) {
+        if (k == 0 && a.mirror_lo) mbase = a.mirror_lo;
+        if (k == g.Z - 1 && a.mirror_hi) mbase = a.mirror_hi;
+      }
 #pragma unroll
       for (int t = 0; t < 2; t++) {
-        const int cr = warp + 8 * t;
-        int y, px;
-        if constexpr (LAT == SPK_SC_26N) {
-          y = y0 + 2 * cr + ((a.c0 >> 1) & 1);
-          px = a.c0 & 1;
-        } else {
-          y = y0 + cr;
-          px = (a.c0 + y + k + g.g0) & 1;
-        }
+        const int y = yrow[t];
+        const int px = LAT == SPK_SC_26N ? (a.c0 & 1) : ((a.c0 + y + k + g.g0) & 1);
+        int32_t *gchunk = kbase + rowoff[t];
+        int32_t *gmirror = mbase ? mbase + rowoff[t] : nullptr;
+        const unsigned long long gsite0 = ksite + rowsite[t];
         if constexpr (PAIR) {
           if (y < Y) {  // warp-uniform; lanes past the row end run along (shuffle) without storing
             const int r = y - y0 + 1;
             const bool valid = x < rowlen;
-            int32_t *gchunk = a.spin + (long long)k * sz + (long long)y * sy + x;
-            int32_t *gmirror = nullptr;
-            if (k == 0 && a.mirror_lo) gmirror = a.mirror_lo + (long long)y * sy + x;
-            if (k == g.Z - 1 && a.mirror_hi) gmirror = a.mirror_hi + (long long)y * sy + x;
-            const unsigned long long gsite0 =
-                ((unsigned long long)(k + g.g0) * g.gY + y) * (unsigned long long)g.gX + x;
             const long long ebase = ((long long)(q0 + s) * sm.nrows + (y >> 1)) * sm.ntx;
             const bool use_left = lane == 0, use_right = valid && (lane == 31 || x + 4 >= rowlen);
             int left_pre = 0, right_new = 0;
@@ -406,12 +417,6 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           }
         } else if (y < Y && x < rowlen) {  // y: warp-uniform
           const int r = y - y0 + 1;
-          int32_t *gchunk = a.spin + (long long)k * sz + (long long)y * sy + x;
-          int32_t *gmirror = nullptr;  // k: CTA-uniform
-          if (k == 0 && a.mirror_lo) gmirror = a.mirror_lo + (long long)y * sy + x;
-          if (k == g.Z - 1 && a.mirror_hi) gmirror = a.mirror_hi + (long long)y * sy + x;
-          const unsigned long long gsite0 =
-              ((unsigned long long)(k + g.g0) * g.gY + y) * (unsigned long long)g.gX + x;
           if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x);
           else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x);
         }
