@@ -231,6 +231,16 @@ int build_tensor_map(spk_cuda_handle *h) {
     cudaGetLastError();
     return 0;
   }
+  // L2 promotion of the box fetches: 64 bytes measured best (potts/pin sc/26n 1024^3: 123.1 Gsites/s;
+  // none / 128 B 122.1; 256 B 120.6 and +5 % DRAM reads: a box row starts 16 bytes before a 128-byte
+  // line, so wide promotion drags in lines of the neighbouring tile that have left L2 again by the
+  // time that tile wants them).  SPK_CUDA_L2PROMO=0..3 (none, 64, 128, 256 bytes) overrides.
+  CUtensorMapL2promotion promo = h->dim == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (const char *e = getenv("SPK_CUDA_L2PROMO")) {
+    const int v = atoi(e);
+    promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+            : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }
   if (h->dim == 2) {  // (element, row) view of the slab, row 0 = lowest ghost row
     const int bh = h->d.lattice == SPK_SQ_4N ? Tile2dCfg<SPK_SQ_4N>::BH
                    : h->d.lattice == SPK_SQ_8N ? Tile2dCfg<SPK_SQ_8N>::BH : Tile2dCfg<SPK_TRI>::BH;
@@ -239,12 +249,12 @@ int build_tensor_map(spk_cuda_handle *h) {
     cuuint32_t box[2] = {(cuuint32_t)T2_BW, (cuuint32_t)bh};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = ((encode_fn)fn)(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, h->base, dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS && h->base_alt)
       r = ((encode_fn)fn)(&h->tmap_alt, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, h->base_alt, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     h->fused2d_ok = (r == CUDA_SUCCESS && h->base_alt);
     return 0;
   }
@@ -253,16 +263,6 @@ int build_tensor_map(spk_cuda_handle *h) {
   cuuint64_t strides[2] = {(cuuint64_t)h->g.X * 4, (cuuint64_t)h->g.X * h->g.Y * 4};
   cuuint32_t box[3] = {(cuuint32_t)ST_BX, (cuuint32_t)rp, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  // L2 promotion of the box fetches: 64 bytes measured best (potts/pin sc/26n 1024^3: 123.1 Gsites/s;
-  // none / 128 B 122.1; 256 B 120.6 and +5 % DRAM reads: a box row starts 16 bytes before a 128-byte
-  // line, so wide promotion drags in lines of the neighbouring tile that have left L2 again by the
-  // time that tile wants them).  SPK_CUDA_L2PROMO=0..3 (none, 64, 128, 256 bytes) overrides.
-  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
-  if (const char *e = getenv("SPK_CUDA_L2PROMO")) {
-    const int v = atoi(e);
-    promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-            : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-  }
   CUresult r = ((encode_fn)fn)(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, h->base, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
