@@ -32,7 +32,11 @@ extern "C" {
 
 /* app_style on the path: AppIsing (src/app_ising.cpp:104-136), AppPotts (src/app_potts.cpp:112-146),
  * AppPottsNeighOnly (src/app_potts_neighonly.cpp:71-117), AppPottsPin (src/app_potts_pin.cpp:93-131) */
-enum { SPK_ISING = 0, SPK_POTTS = 1, SPK_POTTS_NEIGHONLY = 2, SPK_POTTS_PIN = 3 };
+enum { SPK_ISING = 0, SPK_POTTS = 1, SPK_POTTS_NEIGHONLY = 2, SPK_POTTS_PIN = 3,
+       /* variants on the same template: ising/single flips the spin and draws
+        * only for the acceptance (src/app_ising_single.cpp:39-56); potts/neigh picks among maxneigh
+        * bins of which only the distinct neighbour values are events (src/app_potts_neigh.cpp:71-93) */
+       SPK_ISING_SINGLE = 4, SPK_POTTS_NEIGH = 5 };
 /* lattice styles with the reference's enum values (src/lattice.cpp:32-33) */
 enum { SPK_SQ_4N = 2, SPK_SQ_8N = 3, SPK_TRI = 4, SPK_SC_6N = 5, SPK_SC_26N = 6 };
 

@@ -13,9 +13,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 
 SQ_4N, SQ_8N, TRI, SC_6N, SC_26N = 2, 3, 4, 5, 6
-ISING, POTTS, POTTS_NEIGHONLY, POTTS_PIN = 0, 1, 2, 3
+ISING, POTTS, POTTS_NEIGHONLY, POTTS_PIN, ISING_SINGLE, POTTS_NEIGH = 0, 1, 2, 3, 4, 5
 LATTICES = {"sq/4n": SQ_4N, "sq/8n": SQ_8N, "tri": TRI, "sc/6n": SC_6N, "sc/26n": SC_26N}
-MODELS = {"ising": ISING, "potts": POTTS, "potts/neighonly": POTTS_NEIGHONLY, "potts/pin": POTTS_PIN}
+MODELS = {"ising": ISING, "potts": POTTS, "potts/neighonly": POTTS_NEIGHONLY, "potts/pin": POTTS_PIN,
+          "ising/single": ISING_SINGLE, "potts/neigh": POTTS_NEIGH}
 
 IM = 2147483647
 IA = 16807
@@ -116,7 +117,7 @@ class Oracle:
     def __init__(self, model, lattice, nx, ny, nz=1, nspins=2, temperature=0.0):
         self.model = MODELS[model] if isinstance(model, str) else model
         self.lattice = LATTICES[lattice] if isinstance(lattice, str) else lattice
-        if self.model == ISING:
+        if self.model in (ISING, ISING_SINGLE):
             nspins = 2
         self.cfg = Cfg(self.model, self.lattice, nx, ny, nz, nspins, temperature)
         self.L = lib()

@@ -326,7 +326,10 @@ int orc_site_event(const orc_ctx *c, int32_t *spin, int64_t site, orc_draw_fn dr
   int trial;
   if (c->cfg.model == ORC_ISING) {
     trial = draw(state) < 0.5 ? 1 : 2;
-  } else if (c->cfg.model == ORC_POTTS_NEIGHONLY) {
+  } else if (c->cfg.model == ORC_ISING_SINGLE) {
+    /* AppIsingSingle::site_event_rejection (src/app_ising_single.cpp:39-56): flip, no draw here */
+    trial = old == 1 ? 2 : 1;
+  } else if (c->cfg.model == ORC_POTTS_NEIGHONLY || c->cfg.model == ORC_POTTS_NEIGH) {
     /* distinct neighbour values other than my own, in order of first appearance */
     int cand[ORC_MAXNEIGH], ncand = 0;
     for (int n = 0; n < nn; n++) {
@@ -334,10 +337,18 @@ int orc_site_event(const orc_ctx *c, int32_t *spin, int64_t site, orc_draw_fn dr
       for (int q = 0; q < ncand && !seen; q++) seen = (cand[q] == v);
       if (!seen) cand[ncand++] = v;
     }
-    if (ncand == 0) return 0; /* no draw */
-    int pick = (int)(ncand * draw(state));
-    if (pick >= ncand) pick = ncand - 1;
-    trial = cand[pick];
+    if (c->cfg.model == ORC_POTTS_NEIGH) {
+      /* AppPottsNeigh (src/app_potts_neigh.cpp:71-93): the draw is always made; the null bin
+       * extends the candidate list to maxneigh entries */
+      int pick = (int)(nn * draw(state));
+      if (pick >= ncand) return 0;
+      trial = cand[pick];
+    } else {
+      if (ncand == 0) return 0; /* no draw */
+      int pick = (int)(ncand * draw(state));
+      if (pick >= ncand) pick = ncand - 1;
+      trial = cand[pick];
+    }
   } else {
     trial = (int)(Q * draw(state)) + 1;
     if (trial > Q) trial = Q;
@@ -408,7 +419,8 @@ static int philox_event(const orc_ctx *c, int32_t *spin, int64_t site, uint64_t 
   site_ijkm(c, site, &ci, &cj, &ck, &cm);
   uint64_t leader;
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, blk[4], w[2];
-  if (c->cfg.model == ORC_ISING) {
+  const int isinglike = c->cfg.model == ORC_ISING || c->cfg.model == ORC_ISING_SINGLE;
+  if (isinglike) {
     /* ising needs one bit for the trial spin: one block serves the FOUR same-colour sites whose
      * cell index differs only in bits 1,2; site number (i>>1)&3 takes word w of the block:
      * u1 = top bit of w (trial = 1 + bit), u2 = (w mod 2^31)/2^31, i.e. second word = w << 1 */
@@ -418,7 +430,7 @@ static int philox_event(const orc_ctx *c, int32_t *spin, int64_t site, uint64_t 
   }
   uint32_t ctr[4] = {(uint32_t)leader, (uint32_t)(leader >> 32), sweep, (uint32_t)iloop * 16u + (uint32_t)color};
   orc_philox4x32_10(ctr, key, blk);
-  if (c->cfg.model == ORC_ISING) {
+  if (isinglike) { /* ising/single: same word, only its low 31 bits (the acceptance uniform) are used */
     w[0] = blk[(ci >> 1) & 3]; w[1] = w[0] << 1;
   } else {
     const int second = (ci >> 1) & 1;
@@ -431,15 +443,23 @@ static int philox_event(const orc_ctx *c, int32_t *spin, int64_t site, uint64_t 
   int trial;
   if (c->cfg.model == ORC_ISING) {
     trial = w[0] < 0x80000000u ? 1 : 2;
-  } else if (c->cfg.model == ORC_POTTS_NEIGHONLY) {
+  } else if (c->cfg.model == ORC_ISING_SINGLE) {
+    trial = old == 1 ? 2 : 1;
+  } else if (c->cfg.model == ORC_POTTS_NEIGHONLY || c->cfg.model == ORC_POTTS_NEIGH) {
     int cand[ORC_MAXNEIGH], ncand = 0;
     for (int n = 0; n < nn; n++) {
       int v = spin[nb[n]], seen = (v == old);
       for (int q = 0; q < ncand && !seen; q++) seen = (cand[q] == v);
       if (!seen) cand[ncand++] = v;
     }
-    if (ncand == 0) return 0;
-    trial = cand[(int)(((uint64_t)ncand * w[0]) >> 32)];
+    if (c->cfg.model == ORC_POTTS_NEIGH) { /* (int)(maxneigh*u1) = (maxneigh*w) >> 32, null bin beyond ncand */
+      const int pick = (int)(((uint64_t)nn * w[0]) >> 32);
+      if (pick >= ncand) return 0;
+      trial = cand[pick];
+    } else {
+      if (ncand == 0) return 0;
+      trial = cand[(int)(((uint64_t)ncand * w[0]) >> 32)];
+    }
   } else {
     trial = (int)(((uint64_t)Q * w[0]) >> 32) + 1;
   }

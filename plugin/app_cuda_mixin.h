@@ -1,5 +1,6 @@
 /* ----------------------------------------------------------------------
-   SPPARKS app-style plugin: `/cuda` variants of ising, potts, potts/neighonly, potts/pin.
+   SPPARKS app-style plugin: `/cuda` variants of ising, potts, potts/neighonly, potts/pin
+   (and of ising/single, potts/neigh).
 
    Drop these files into the SPPARKS src/ directory (or add them to the build as
    plugin/Makefile does), rebuild, and `app_style potts/cuda 100` runs the rejection-KMC
@@ -45,7 +46,7 @@ class AppCudaMixin : public Base, public SpkCudaHost {
   {
     // Base parsed its arguments only if style matched its own name
     // (src/app_potts.cpp:47, src/app_potts_neighonly.cpp:36), so do it here
-    if constexpr (MODEL == SPK_ISING) {
+    if constexpr (MODEL == SPK_ISING || MODEL == SPK_ISING_SINGLE) {
       if (narg != 1) this->error->all(FLERR,"Illegal app_style command");
       nspins_cuda = 2;
     } else {

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPK_CUDA_LIB selects another build of the same library (kernel A/B experiments only)
 LIB_PATH = os.environ.get("SPK_CUDA_LIB") or os.path.join(_HERE, "lib", "libspparks_cuda.so")
 
-ISING, POTTS, POTTS_NEIGHONLY, POTTS_PIN = 0, 1, 2, 3
+ISING, POTTS, POTTS_NEIGHONLY, POTTS_PIN, ISING_SINGLE, POTTS_NEIGH = 0, 1, 2, 3, 4, 5
 SQ_4N, SQ_8N, TRI, SC_6N, SC_26N = 2, 3, 4, 5, 6
 COMM_ID_BYTES = 128
 

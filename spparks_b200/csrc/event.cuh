@@ -51,11 +51,15 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 //   ising:        four sites per block (cells differing in bits 1,2): the trial spin needs one
 //                 bit only, so site (i>>1)&3 takes ONE word w: u1 = its top bit, u2 = (w mod 2^31)/2^31,
 //                 expressed as second word = w << 1 so that `w2 > thr` is unchanged
+// the two-state apps (one Philox word per site) and the candidate-list apps
+__host__ __device__ constexpr bool ising_like(int model) { return model == SPK_ISING || model == SPK_ISING_SINGLE; }
+__host__ __device__ constexpr bool neigh_like(int model) { return model == SPK_POTTS_NEIGHONLY || model == SPK_POTTS_NEIGH; }
+
 template <int MODEL> __device__ __forceinline__ int philox_leader_shift(int i) {
-  return MODEL == SPK_ISING ? (i & 6) : (i & 2);  // cells between the site and its block leader
+  return ising_like(MODEL) ? (i & 6) : (i & 2);  // cells between the site and its block leader
 }
 template <int MODEL> __device__ __forceinline__ void philox_words(const uint4 &blk, int i, uint32_t &w1, uint32_t &w2) {
-  if (MODEL == SPK_ISING) {
+  if (ising_like(MODEL)) {
     const int s = (i >> 1) & 3;
     w1 = s == 0 ? blk.x : (s == 1 ? blk.y : (s == 2 ? blk.z : blk.w));
     w2 = w1 << 1;
@@ -222,7 +226,7 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
   const int Q = p.nspins;
   if (MODEL == SPK_POTTS_PIN && old > Q) return old;  // pinned: no draw (src/app_potts_pin.cpp:97)
 
-  constexpr bool PK = P16 && MODEL != SPK_ISING;
+  constexpr bool PK = P16 && !ising_like(MODEL);
   uint32_t negp[PK ? NN / 2 : 1];
   if constexpr (PK) {
 #pragma unroll
@@ -233,26 +237,41 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
   else e0 = unlike<NN>(v, old, p.one);
   int trial;
 
-  if constexpr (MODEL == SPK_POTTS_NEIGHONLY) {
+  if constexpr (neigh_like(MODEL)) {
     // candidates = distinct neighbour values != old, first-occurrence order
-    // (src/app_potts_neighonly.cpp:81-88); bit n of `first` marks slot n as a new candidate
-    if (e0 == 0) return old;  // nevent == 0: no draw (src/app_potts_neighonly.cpp:90)
+    // (src/app_potts_neighonly.cpp:81-88, src/app_potts_neigh.cpp:79-87); bit n of `first` marks
+    // slot n as a new candidate.  potts/neighonly picks among the nevent candidates and draws
+    // nothing when there is none (:90); potts/neigh ALWAYS draws and picks among maxneigh bins,
+    // the bins beyond nevent being null events (src/app_potts_neigh.cpp:89-91)
+    constexpr bool NULLBIN = MODEL == SPK_POTTS_NEIGH;
+    double u = 0.0;
+    if constexpr (NULLBIN && RNG != RNG_PHILOX) {
+      if constexpr (RNG == RNG_INJECTED) u = d.u1;
+      else u = park_uniform(d.seed);
+    }
+    if (e0 == 0) return old;  // nevent == 0: no event (neighonly: no draw either)
     uint32_t first;
     if constexpr (PK) first = first_occurrence_mask16<NN>(v, negp, old, p);
     else first = first_occurrence_mask<NN>(v, old);
     const int nevent = __popc(first);
     int pick;
     if constexpr (RNG == RNG_PHILOX) {
-      pick = (int)__umulhi((uint32_t)nevent, d.w1);
+      pick = (int)__umulhi((uint32_t)(NULLBIN ? NN : nevent), d.w1);
+    } else if constexpr (NULLBIN) {
+      pick = (int)(NN * u);
     } else {
-      double u;
       if constexpr (RNG == RNG_INJECTED) u = d.u1;
       else u = park_uniform(d.seed);
       pick = (int)(nevent * u);
       if (pick >= nevent) pick = nevent - 1;
     }
+    if constexpr (NULLBIN) {
+      if (pick >= nevent) return old;
+    }
     if constexpr (PK) trial = select_slot16<NN>(negp, nth_set_bit(first, pick));
     else trial = select_slot<NN>(v, nth_set_bit(first, pick));
+  } else if constexpr (MODEL == SPK_ISING_SINGLE) {
+    trial = 3 - old;  // spins are 1 or 2 (src/app_ising_single.cpp:46-47)
   } else if constexpr (RNG == RNG_PHILOX) {
     if (MODEL == SPK_ISING) trial = (d.w1 < 0x80000000u) ? 1 : 2;
     else trial = (int)__umulhi((uint32_t)Q, d.w1) + 1;
@@ -273,9 +292,10 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
   if constexpr (NN > 8) {
     if (e0 == NN) return trial;
   }
-  if constexpr (MODEL == SPK_ISING) {
+  if constexpr (ising_like(MODEL)) {
     // two-state shortcut: with spins in {1,2} the neighbours unlike `old` are exactly the ones
     // like a different trial, so efinal = NN - einitial and no second count is needed
+    // (ising/single: the trial always differs and its acceptance draw is the event's first draw)
     const int dE2 = NN - 2 * e0;
     if constexpr (RNG == RNG_PHILOX) {
       // branch-free: thr[0] = 2^32-1 accepts every dE <= 0; T = 0 has thr[dE>0] = 0 and must
@@ -287,7 +307,7 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
       if (dE2 <= 0) return trial;
       if (p.t_zero) return old;
       double u;
-      if constexpr (RNG == RNG_INJECTED) u = d.u2;
+      if constexpr (RNG == RNG_INJECTED) u = MODEL == SPK_ISING_SINGLE ? d.u1 : d.u2;
       else u = park_uniform(d.seed);
       return u > p.ptab[dE2] ? old : trial;
     }

@@ -137,7 +137,7 @@ void build_tables(spk_cuda_handle *h) {
   // exp((einitial-efinal)*t_inverse) of site_event_rejection (src/app_potts.cpp:130), evaluated
   // with the host libm for every possible integer dE so that device results are bit-identical
   EventParams &ev = h->ev;
-  ev.nspins = h->d.model == SPK_ISING ? 2 : h->d.nspins;
+  ev.nspins = ising_like(h->d.model) ? 2 : h->d.nspins;
   ev.t_zero = h->d.temperature == 0.0;
   ev.one = 1;
   ev.k0 = (uint32_t)h->d.seed;
@@ -347,6 +347,8 @@ template <int LAT> int fused_sweep_l(spk_cuda_handle *h, const SweepArgs &a, int
     case SPK_POTTS: return launch_tile2d<LAT, SPK_POTTS>(h, a, part);
     case SPK_POTTS_NEIGHONLY: return launch_tile2d<LAT, SPK_POTTS_NEIGHONLY>(h, a, part);
     case SPK_POTTS_PIN: return launch_tile2d<LAT, SPK_POTTS_PIN>(h, a, part);
+    case SPK_ISING_SINGLE: return launch_tile2d<LAT, SPK_ISING_SINGLE>(h, a, part);
+    case SPK_POTTS_NEIGH: return launch_tile2d<LAT, SPK_POTTS_NEIGH>(h, a, part);
   }
   return -1;
 }
@@ -379,7 +381,7 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
   if constexpr (LAT != SPK_SC_26N && LAT != SPK_SC_6N) {
     return -1;
   } else {
-    if (pair && (LAT != SPK_SC_26N || MODEL == SPK_ISING || (a.c0 & 1) || a.nloop != 1)) return -1;
+    if (pair && (LAT != SPK_SC_26N || ising_like(MODEL) || (a.c0 & 1) || a.nloop != 1)) return -1;
     using C = StreamCfg<LAT>;
     const Geo &g = a.g;
     const Box &b = a.b;
@@ -409,8 +411,8 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
     SweepArgs args = a;  // Geo::lo_wrap / hi_wrap select periodic images (1 GPU) or ghost planes (slabs)
     // P16: packed 16-bit compares (event.cuh) when every spin fits; the Ising shortcut has no compares to pack
     auto launch = [&](auto ONE, auto PK, auto PAIR) -> int {
-      constexpr bool one = decltype(ONE)::value, pk = decltype(PK)::value && MODEL != SPK_ISING;
-      constexpr bool pr = decltype(PAIR)::value && one && LAT == SPK_SC_26N && MODEL != SPK_ISING;
+      constexpr bool one = decltype(ONE)::value, pk = decltype(PK)::value && !ising_like(MODEL);
+      constexpr bool pr = decltype(PAIR)::value && one && LAT == SPK_SC_26N && !ising_like(MODEL);
       if constexpr (pr) {  // tile-edge words first (stream order: they see the lattice before the pair launch)
         sm.nrows = g.Y / 2;
         const size_t words = 2 * (size_t)sm.ntx * sm.nrows * sm.nq;
@@ -487,7 +489,7 @@ template <int MODEL> int sweep_pair_m(spk_cuda_handle *h, int color, const int32
 }
 
 bool pair_ok(const spk_cuda_handle *h) {
-  return h->use_pair && h->tiled && h->use_stream && h->stream_ok && h->d.lattice == SPK_SC_26N && h->d.model != SPK_ISING;
+  return h->use_pair && h->tiled && h->use_stream && h->stream_ok && h->d.lattice == SPK_SC_26N && !ising_like(h->d.model);
 }
 
 int sweep_pair(spk_cuda_handle *h, int color, const int32_t *box) {
@@ -496,6 +498,7 @@ int sweep_pair(spk_cuda_handle *h, int color, const int32_t *box) {
     case SPK_POTTS: rc = sweep_pair_m<SPK_POTTS>(h, color, box); break;
     case SPK_POTTS_NEIGHONLY: rc = sweep_pair_m<SPK_POTTS_NEIGHONLY>(h, color, box); break;
     case SPK_POTTS_PIN: rc = sweep_pair_m<SPK_POTTS_PIN>(h, color, box); break;
+    case SPK_POTTS_NEIGH: rc = sweep_pair_m<SPK_POTTS_NEIGH>(h, color, box); break;
     default: break;
   }
   if (rc > 0) return fail("colour-pair launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -509,6 +512,8 @@ template <int LAT> int sweep_set_l(spk_cuda_handle *h, int rng, int color, const
     case SPK_POTTS: return sweep_set_lm<LAT, SPK_POTTS>(h, rng, color, box, nloop);
     case SPK_POTTS_NEIGHONLY: return sweep_set_lm<LAT, SPK_POTTS_NEIGHONLY>(h, rng, color, box, nloop);
     case SPK_POTTS_PIN: return sweep_set_lm<LAT, SPK_POTTS_PIN>(h, rng, color, box, nloop);
+    case SPK_ISING_SINGLE: return sweep_set_lm<LAT, SPK_ISING_SINGLE>(h, rng, color, box, nloop);
+    case SPK_POTTS_NEIGH: return sweep_set_lm<LAT, SPK_POTTS_NEIGH>(h, rng, color, box, nloop);
   }
   return fail("unknown model %d", h->d.model);
 }
@@ -568,7 +573,7 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
   *out = nullptr;
   const int nn = spk_cuda_maxneigh(desc->lattice);
   if (!nn) return fail("unsupported lattice style %d", desc->lattice);
-  if (desc->model < SPK_ISING || desc->model > SPK_POTTS_PIN) return fail("unsupported app model %d", desc->model);
+  if (desc->model < SPK_ISING || desc->model > SPK_POTTS_NEIGH) return fail("unsupported app model %d", desc->model);
   const int dim = lat_dim(desc->lattice);
   const int nz = dim == 3 ? desc->nz : 1;
   if (desc->nx < 2 || desc->ny < 2 || nz < 1) return fail("lattice extents must be >= 2");
@@ -576,7 +581,7 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
   // tri only needs nx even
   if (desc->nx % 2 || (desc->lattice != SPK_TRI && desc->ny % 2) || (dim == 3 && nz % 2))
     return fail("Color stencil is incommensurate with lattice size");
-  if (desc->model != SPK_ISING && desc->nspins <= 0) return fail("Illegal app_style command: nspins must be > 0");
+  if (!ising_like(desc->model) && desc->nspins <= 0) return fail("Illegal app_style command: nspins must be > 0");
   if (desc->temperature < 0.0) return fail("temperature must be >= 0");
   if (desc->nranks < 1 || desc->rank < 0 || desc->rank >= desc->nranks) return fail("bad rank/nranks");
   const int nslab_g = dim == 3 ? nz : desc->ny;
@@ -613,7 +618,7 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
   h->use_pair = pairenv && pairenv[0] == '1';
   const char *np = getenv("SPK_CUDA_NO_PK16");
   // spins are 1..Q (potts/pin: Q+1 marks a pinned site, src/app_potts_pin.cpp:81)
-  h->pk16 = !(np && np[0] == '1') && desc->model != SPK_ISING &&
+  h->pk16 = !(np && np[0] == '1') && !ising_like(desc->model) &&
             (int64_t)desc->nspins + (desc->model == SPK_POTTS_PIN ? 1 : 0) <= PK16_MAX_SPIN;
   build_tables(h);
 
@@ -694,7 +699,7 @@ int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n) {
   h->ghosts_valid = false;
   // the reference's init_app refuses spins outside 1..Q (Q+1 = pinned for potts/pin); the kernels
   // rely on it (packed 16-bit compares), so the check is repeated where the spins enter the device
-  const int hi = h->d.model == SPK_ISING ? 2 : h->d.nspins + (h->d.model == SPK_POTTS_PIN ? 1 : 0);
+  const int hi = ising_like(h->d.model) ? 2 : h->d.nspins + (h->d.model == SPK_POTTS_PIN ? 1 : 0);
   CU(cudaMemsetAsync(h->escratch, 0, sizeof(unsigned long long), h->stream));
   validate_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, n, 1, hi, h->escratch);
   h->launches++;

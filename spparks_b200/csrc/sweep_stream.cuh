@@ -151,7 +151,7 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
   int accepted = 0;
   // Philox block of the chunk's two class sites (event.cuh: philox_words); an ising block spans
   // two chunks, this one is its upper half when bit 2 of the (4-aligned) chunk start is set
-  const bool upper = MODEL == SPK_ISING ? ((xcell >> 2) & 1) : false;
+  const bool upper = ising_like(MODEL) ? ((xcell >> 2) & 1) : false;
   const unsigned long long leader = gsite0 + P - (upper ? 4 : 0);
   const int nloop = ONEPASS ? 1 : a.nloop;  // ONEPASS: the common nloop == 1 without loop overhead
 #pragma unroll
@@ -167,7 +167,7 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
         v[n] = W[(o.dz + 1) * 3 + (o.dy + 1)][1 + e + o.dx];
       });
       Draws<RNG_PHILOX> d;
-      if constexpr (MODEL == SPK_ISING) {
+      if constexpr (ising_like(MODEL)) {
         d.w1 = upper ? (h ? blk.w : blk.z) : (h ? blk.y : blk.x);
         d.w2 = d.w1 << 1;
       } else {

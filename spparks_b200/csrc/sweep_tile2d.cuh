@@ -70,11 +70,11 @@ __device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t 
     before[s] = cur[s] = Wc[4 + P + S * s];
   });
   int accepted = 0;
-  constexpr int SPB = (MODEL == SPK_ISING) ? 4 : 2;  // class sites per Philox block (event.cuh)
+  constexpr int SPB = ising_like(MODEL) ? 4 : 2;  // class sites per Philox block (event.cuh)
   constexpr int NBLK = (NS + SPB - 1) / SPB;
   static_for<NBLK>([&](auto PR) {
     constexpr int pr = decltype(PR)::value;
-    const bool upper = (MODEL == SPK_ISING && NS < SPB) ? ((xg >> 3) & 1) : false;
+    const bool upper = (ising_like(MODEL) && NS < SPB) ? ((xg >> 3) & 1) : false;
     const unsigned long long leader = grow + P + S * (SPB * pr) - (upper ? 8 : 0);
     const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep, (uint32_t)(c0 + 1),
                                     a.ev.rk);
@@ -87,7 +87,7 @@ __device__ __forceinline__ int tile2d_strip(const SweepArgs &a, int c0, int32_t 
         v[n] = (o.dy < 0 ? Wm : (o.dy > 0 ? Wp : Wc))[4 + p + R::delta(n)];
       });
       Draws<RNG_PHILOX> d;
-      if constexpr (MODEL == SPK_ISING) {
+      if constexpr (ising_like(MODEL)) {
         const uint32_t lo = h == 0 ? blk.x : (h == 1 ? blk.y : (h == 2 ? blk.z : blk.w));
         const uint32_t hi = h == 0 ? blk.z : blk.w;
         d.w1 = upper ? hi : lo;

@@ -115,12 +115,12 @@ __device__ __forceinline__ int strip_body(const SweepArgs &a, int e0, int j, int
   for (int l = 0; l < a.nloop; l++) {
     // Philox blocks of the strip (event.cuh: philox_words): potts family one block per pair of
     // class sites, ising one block per four
-    constexpr int SPB = (MODEL == SPK_ISING) ? 4 : 2;           // class sites per block
+    constexpr int SPB = ising_like(MODEL) ? 4 : 2;           // class sites per block
     constexpr int NBLK = (NS + SPB - 1) / SPB;                  // blocks the strip touches
     static_for<NBLK>([&](auto PR) {
       constexpr int pr = decltype(PR)::value;
       // strips are 8-element aligned; a tri strip (4 cells) is half of an ising block
-      const bool upper = (MODEL == SPK_ISING && NS < SPB) ? ((e0 >> 3) & 1) : false;
+      const bool upper = (ising_like(MODEL) && NS < SPB) ? ((e0 >> 3) & 1) : false;
       const unsigned long long leader = grow + P + S * (SPB * pr) - (upper ? 8 : 0);
       const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep,
                                       (uint32_t)l * 16u + (uint32_t)(a.c0 + 1), a.ev.rk);
@@ -134,7 +134,7 @@ __device__ __forceinline__ int strip_body(const SweepArgs &a, int e0, int j, int
           v[n] = W[row][idx];
         });
         Draws<RNG_PHILOX> d;
-        if constexpr (MODEL == SPK_ISING) {
+        if constexpr (ising_like(MODEL)) {
           const uint32_t lo = h == 0 ? blk.x : (h == 1 ? blk.y : (h == 2 ? blk.z : blk.w));
           const uint32_t hi = h == 0 ? blk.z : blk.w;  // (only h < 2 when the strip is the upper half)
           d.w1 = upper ? hi : lo;

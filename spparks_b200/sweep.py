@@ -6,7 +6,7 @@ import numpy as np
 from . import _lib
 
 MODELS = {"ising": _lib.ISING, "potts": _lib.POTTS, "potts/neighonly": _lib.POTTS_NEIGHONLY,
-          "potts/pin": _lib.POTTS_PIN}
+          "potts/pin": _lib.POTTS_PIN, "ising/single": _lib.ISING_SINGLE, "potts/neigh": _lib.POTTS_NEIGH}
 LATTICES = {"sq/4n": _lib.SQ_4N, "sq/8n": _lib.SQ_8N, "tri": _lib.TRI, "sc/6n": _lib.SC_6N,
             "sc/26n": _lib.SC_26N}
 

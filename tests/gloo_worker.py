@@ -45,7 +45,7 @@ def main():
     for model, lat, n, q, T in cases:
         o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
         rng = np.random.default_rng(3)
-        spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=o.nsites, dtype=np.int32)
+        spins = rng.integers(1, (2 if model.startswith("ising") else q) + 1, size=o.nsites, dtype=np.int32)
         want = spins.copy()
         for sw in range(3):
             o.sweep_philox(want, 99, sw)

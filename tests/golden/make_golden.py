@@ -27,7 +27,10 @@ DIM = {"sq/4n": 2, "sq/8n": 2, "tri": 2, "sc/6n": 3, "sc/26n": 3}
 NBASIS = {"sq/4n": 1, "sq/8n": 1, "tri": 2, "sc/6n": 1, "sc/26n": 1}
 NCOLORS = {"sq/4n": 2, "sq/8n": 4, "tri": 4, "sc/6n": 2, "sc/26n": 8}
 DT_SWEEP = {"ising": lambda q, mn: 0.5, "potts": lambda q, mn: 1.0 / q,
-            "potts/pin": lambda q, mn: 1.0 / q, "potts/neighonly": lambda q, mn: 1.0 / mn}
+            "potts/pin": lambda q, mn: 1.0 / q, "potts/neighonly": lambda q, mn: 1.0 / mn,
+            # src/app_ising_single.cpp:29, src/app_potts_neigh.cpp:47
+            "ising/single": lambda q, mn: 1.0, "potts/neigh": lambda q, mn: 1.0 / mn}
+ISING_LIKE = ("ising", "ising/single")
 MAXNEIGH = {"sq/4n": 4, "sq/8n": 8, "tri": 6, "sc/6n": 6, "sc/26n": 26}
 
 
@@ -37,11 +40,11 @@ def tag(s):
 
 def header(model, q, lattice, n, seed=12345):
     nx, ny, nz = n
-    app = "ising" if model == "ising" else "%s %d" % (model, q)
+    app = model if model in ISING_LIKE else "%s %d" % (model, q)
     zreg = "0 %d" % nz if DIM[lattice] == 3 else "-0.5 0.5"
     return ["seed %d" % seed, "app_style %s" % app, "dimension %d" % DIM[lattice],
             "lattice %s 1.0" % lattice, "region box block 0 %d 0 %d %s" % (nx, ny, zreg),
-            "create_box box", "create_sites box", "set site range 1 %d" % (2 if model == "ising" else q)]
+            "create_box box", "create_sites box", "set site range 1 %d" % (2 if model in ISING_LIKE else q)]
 
 
 def run_driver(lines, tmp):
@@ -77,7 +80,7 @@ def gen_geom(lattice, n):
 
 
 def random_spins(rng, model, q, ns, pinfrac=0.0, blocky=False):
-    hi = 2 if model == "ising" else q
+    hi = 2 if model in ISING_LIKE else q
     s = rng.integers(1, hi + 1, size=ns, dtype=np.int32)
     if blocky:  # long runs of equal spins so that neighonly meets few/zero candidates
         s = np.repeat(rng.integers(1, hi + 1, size=(ns + 15) // 16, dtype=np.int32), 16)[:ns].copy()
@@ -179,5 +182,25 @@ def main():
     print("wrote", len([f for f in os.listdir(HERE) if f.endswith(".npz")]), "fixtures")
 
 
+def main_variants():
+    """ising/single and potts/neigh (own random stream, so that the fixtures of
+    main() stay byte-identical):  python tests/golden/make_golden.py variants"""
+    rng = np.random.default_rng(20261018)
+    for T in (0.0, 1.0):
+        gen_half("ising/single", 2, "sq/4n", (16, 12, 1), T, rng)
+        gen_half("potts/neigh", 6, "sc/26n", (8, 6, 10), T, rng)
+    gen_half("ising/single", 2, "sc/26n", (8, 6, 10), 6.0, rng)
+    gen_half("potts/neigh", 4, "tri", (8, 10, 1), 0.6, rng)
+    gen_half("potts/neigh", 3, "sc/26n", (8, 6, 10), 0.7, rng, blocky=True)
+    gen_half("potts/neigh", 3, "sq/8n", (12, 10, 1), 0.5, rng)
+    gen_sets("potts/neigh", 5, "sc/26n", (8, 6, 10), 0.8, rng)
+    gen_strict("ising/single", 2, "sq/4n", (16, 12, 1), 1.1346, 5, rng)
+    gen_strict("potts/neigh", 9, "sc/26n", (6, 6, 8), 0.5, 4, rng)
+    gen_strict("potts/neigh", 5, "tri", (8, 8, 1), 0.4, 6, rng)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        main_variants()
+    else:
+        main()

@@ -19,6 +19,7 @@ CASES = [
     ("potts", "sc/26n", (32, 16, 24), 20, 0.6),
     ("potts/neighonly", "sc/26n", (24, 12, 16), 50, 0.5),
     ("potts/pin", "sc/26n", (16, 16, 8), 9, 0.9),
+    ("potts/neigh", "sc/26n", (16, 12, 8), 6, 0.6),
     ("ising", "sc/6n", (16, 8, 16), 2, 2.2),
     ("ising", "sq/4n", (64, 32, 1), 2, 1.13),
     ("potts", "tri", (40, 24, 1), 7, 0.5),
@@ -37,7 +38,7 @@ def main():
         nb = NBASIS.get(lat, 1)
         nsites = n[0] * n[1] * n[2] * nb
         rng = np.random.default_rng(42)
-        spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=nsites, dtype=np.int32)
+        spins = rng.integers(1, (2 if model.startswith("ising") else q) + 1, size=nsites, dtype=np.int32)
         if model == "potts/pin":
             spins[rng.random(nsites) < 0.05] = q + 1
         s = LatticeSweep(model, lat, n[0], n[1], n[2], nspins=q, temperature=T, seed=777, device=local,

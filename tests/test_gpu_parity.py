@@ -113,6 +113,16 @@ CASES = [
     ("potts", "tri", (252, 66, 1), 9, 0.5),
     ("potts/neighonly", "tri", (124, 10, 1), 4, 0.6),
     ("potts/pin", "sq/8n", (128, 64, 1), 8, 0.8),
+    # the variants on the same template, through every kernel family
+    ("ising/single", "sq/4n", (64, 48, 1), 2, 1.2),
+    ("ising/single", "sq/4n", (496, 130, 1), 2, 1.1346),
+    ("ising/single", "sc/26n", (16, 12, 10), 2, 6.0),
+    ("ising/single", "sc/6n", (24, 10, 14), 2, 2.2),
+    ("potts/neigh", "sc/26n", (20, 12, 14), 50, 0.5),
+    ("potts/neigh", "sc/26n", (132, 34, 12), 5, 0.5),
+    ("potts/neigh", "sc/26n", (16, 12, 10), 70000, 0.0),
+    ("potts/neigh", "tri", (252, 66, 1), 4, 0.6),
+    ("potts/neigh", "sq/8n", (40, 22, 1), 3, 0.7),
     # largest Q of the packed 16-bit compare path (spins <= 65534) and the first Q beyond it
     ("potts/neighonly", "sc/26n", (16, 12, 10), 65534, 0.5),
     ("potts/pin", "sc/26n", (16, 12, 10), 65533, 0.5),
@@ -138,7 +148,7 @@ def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, kernel, monkeypa
         monkeypatch.setenv("SPK_CUDA_NO_FUSED", "1")
     rng = np.random.default_rng(7)
     o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
-    spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=o.nsites, dtype=np.int32)
+    spins = rng.integers(1, (2 if model.startswith("ising") else q) + 1, size=o.nsites, dtype=np.int32)
     if model == "potts/pin":
         spins[rng.random(o.nsites) < 0.05] = q + 1
     s = _sweep(model, lat, n, q, T, seed=0xC0FFEE12345)
@@ -215,7 +225,7 @@ def test_edge_sizes_and_errors():
                              ("potts", "tri", (2, 2, 1), 4), ("potts/neighonly", "sq/8n", (2, 2, 1), 3)]:
         o = O.Oracle(model, lat, n[0], n[1], n[2], q, 0.8)
         rng = np.random.default_rng(3)
-        spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=o.nsites, dtype=np.int32)
+        spins = rng.integers(1, (2 if model.startswith("ising") else q) + 1, size=o.nsites, dtype=np.int32)
         s = _sweep(model, lat, n, q, 0.8, seed=5)
         s.upload(spins)
         want = spins.copy()
@@ -264,7 +274,7 @@ def test_large_lattices_bit_exact_vs_oracle(model, lat, n, q, T):
     already been stored (catches in-place halo hazards that small lattices cannot show)."""
     rng = np.random.default_rng(21)
     o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
-    spins = rng.integers(1, (2 if model == "ising" else q) + 1, size=o.nsites, dtype=np.int32)
+    spins = rng.integers(1, (2 if model.startswith("ising") else q) + 1, size=o.nsites, dtype=np.int32)
     s = _sweep(model, lat, n, q, T, seed=777)
     s.upload(spins)
     want = spins.copy()

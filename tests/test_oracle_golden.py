@@ -10,7 +10,8 @@ import oracle_py as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 LAT = {"sq_4n": "sq/4n", "sq_8n": "sq/8n", "tri": "tri", "sc_6n": "sc/6n", "sc_26n": "sc/26n"}
-MODEL = {"ising": "ising", "potts": "potts", "potts_neighonly": "potts/neighonly", "potts_pin": "potts/pin"}
+MODEL = {"ising": "ising", "potts": "potts", "potts_neighonly": "potts/neighonly", "potts_pin": "potts/pin",
+         "ising_single": "ising/single", "potts_neigh": "potts/neigh"}
 
 
 def split_name(path, prefix):

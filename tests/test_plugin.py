@@ -73,6 +73,10 @@ STRICT_CASES = [
     dict(app="ising", q=0, dim=2, lat="sq/4n", nx=64, ny=32, zr="-0.5 0.5", hi=2, T=1.1346, stats=2.0, run=10.0,
          extra=""),
     dict(app="potts", q=9, dim=2, lat="tri", nx=16, ny=10, zr="-0.5 0.5", hi=9, T=0.5, stats=0.5, run=1.0, extra=""),
+    dict(app="ising/single", q=0, dim=2, lat="sq/4n", nx=48, ny=32, zr="-0.5 0.5", hi=2, T=1.3, stats=4.0, run=20.0,
+         extra=""),
+    dict(app="potts/neigh", q=15, dim=3, lat="sc/26n", nx=12, ny=8, zr="0 10", hi=15, T=0.6, stats=0.5, run=1.0,
+         extra=""),
 ]
 
 
@@ -82,7 +86,7 @@ def test_color_strict_script_identical_to_reference(case):
     the same script must print the same Naccept / Nreject / Nsweeps / Energy table, over two
     consecutive `run` commands."""
     def script(style):
-        app = style if case["app"] == "ising" else "%s %d" % (style, case["q"])
+        app = style if case["app"].startswith("ising") else "%s %d" % (style, case["q"])
         return STRICT.format(**dict(case, app=app))
     ref = stats_rows(run(SPK_REF, script(case["app"])))
     gpu = stats_rows(run(SPK_CUDA, script(case["app"] + "/cuda")))
