@@ -300,7 +300,17 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
     if constexpr (RNG == RNG_PHILOX) {
       // branch-free: thr[0] = 2^32-1 accepts every dE <= 0; T = 0 has thr[dE>0] = 0 and must
       // not accept on w2 == 0, hence the explicit t_zero term
-      const bool ok = (dE2 <= 0) || (!p.t_zero && d.w2 <= p.thr[dE2 > 0 ? dE2 : 0]);
+      uint32_t thr;
+      if constexpr (NN <= 8) {
+        // dE2 > 0 takes the values 2, 4, ..., NN only: a select chain over constant-bank operands
+        // instead of a dynamically indexed constant load (LDC: long-scoreboard latency per site)
+        thr = p.thr[NN];
+#pragma unroll
+        for (int dE = NN - 2; dE >= 2; dE -= 2) thr = dE2 == dE ? p.thr[dE] : thr;
+      } else {
+        thr = p.thr[dE2 > 0 ? dE2 : 0];
+      }
+      const bool ok = (dE2 <= 0) || (!p.t_zero && d.w2 <= thr);
       return ok ? trial : old;
     } else {
       if (trial == old) return old;
