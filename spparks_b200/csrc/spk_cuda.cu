@@ -401,7 +401,10 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
     sm.kfirst = kfirst;
     sm.nq = nq;
     const int grid_max = 2 * 148;
-    int nzc = (8 * grid_max + sm.ntx * sm.nty - 1) / (sm.ntx * sm.nty);
+    // work items per resident CTA (plane chunks are cut so that there are about this many): more
+    // items balance the tail better, fewer re-read fewer chunk-boundary planes (SPK_CUDA_ITEMS_PER_CTA, A/B tests)
+    static const int items_per_cta = [] { const char *e = getenv("SPK_CUDA_ITEMS_PER_CTA"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+    int nzc = (items_per_cta * grid_max + sm.ntx * sm.nty - 1) / (sm.ntx * sm.nty);
     if (nzc > nq) nzc = nq;
     if (nzc < 1) nzc = 1;
     sm.qchunk = (nq + nzc - 1) / nzc;
