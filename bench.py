@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
@@ -178,12 +178,16 @@ def cpu_reference(w, warm, steps, cores=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    # 200 sweeps of the default workload are 0.18 s of device time: long enough for the clock sampler
+    # (one nvidia-smi sample per 20 ms) to see the timed region several times
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--size", type=int, nargs=3, default=None, help="override the per-GPU lattice (debug)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-segment", type=int, default=20,
+                    help="sweeps per host round trip of the e2e leg (examples/ising/in.ising: `stats 10.0` = 20 sweeps)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the other_workloads leg")
     args = ap.parse_args()
@@ -289,15 +293,16 @@ def main():
     value = natt_all / (ms * 1e-3) / 1e9
 
     # ---- e2e: the public C ABI with HOST buffers, as the SPPARKS plugin drives it for one `run`
-    # segment of K sweeps (plugin/app_cuda_mixin.h iterate_rejection): pinned H2D of the lattice,
-    # K sweeps each followed by a D2H read of the step's metric (accept/attempt counters), then D2H
+    # segment of --e2e-segment (20) sweeps (plugin/app_cuda_mixin.h iterate_rejection): pinned H2D of the lattice,
+    # the sweeps, each followed by a D2H read of the step's metric (accept/attempt counters), then D2H
     # of the lattice for the host-side output.  All copies are inside the timed region (wall clock).
     host = torch.empty(s.nlocal, dtype=torch.int32).pin_memory()
     s.download_ptr(host.data_ptr(), s.nlocal)
     barrier(s)
     t0 = time.perf_counter()
     s.upload_ptr(host.data_ptr(), s.nlocal)
-    for _ in range(args.steps):
+    seg = max(1, args.e2e_segment)
+    for _ in range(seg):
         s.sweeps(sweep_no, 1)
         sweep_no += 1
         s.counters()
@@ -318,7 +323,7 @@ def main():
     te = torch.tensor([e2e_s, strict_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = s.nlocal * world * args.steps / float(te[0].item()) / 1e9
+    e2e_value = s.nlocal * world * seg / float(te[0].item()) / 1e9
     strict_value = s.nlocal * world * args.e2e_steps / float(te[1].item()) / 1e9
 
     if rank == 0:
@@ -348,11 +353,12 @@ def main():
                              "avg_launch_ms": avg_launch_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
                              "colour_fused_bound_bytes_per_site": 8},
                 "e2e": {"value": e2e_value, "unit": "Gsites/s",
-                        "h2d_bytes_per_step": 4 * s.nlocal * world / args.steps,
-                        "d2h_bytes_per_step": (4 * s.nlocal * world) / args.steps + 16 * world,
+                        "h2d_bytes_per_step": 4 * s.nlocal * world / seg,
+                        "d2h_bytes_per_step": (4 * s.nlocal * world) / seg + 16 * world,
                         "definition": "one run segment through the C ABI as the SPPARKS plugin issues it: pinned H2D "
                                       "of the lattice, %d sweeps each followed by a D2H read of the counters, D2H of "
-                                      "the lattice; bytes are the segment's copies divided by its sweeps" % args.steps,
+                                      "the lattice; bytes are the segment's copies divided by its sweeps (segment length as "
+                                      "in examples/ising/in.ising: one stats line per 20 sweeps)" % seg,
                         "strict_per_step": {"value": strict_value, "unit": "Gsites/s", "steps": args.e2e_steps,
                                             "h2d_bytes_per_step": 4 * s.nlocal * world,
                                             "d2h_bytes_per_step": 4 * s.nlocal * world + 16 * world,
