@@ -992,22 +992,6 @@ int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
   const bool overlap = h->dim == 3 || (fused2d && getenv("SPK_CUDA_OVERLAP_2D"));
   if (h->d.nranks > 1 && h->comm && nsweeps > 0 && overlap && !getenv("SPK_CUDA_NO_OVERLAP"))
     return sweeps_overlapped(h, first_sweep, nsweeps);
-  if (h->d.nranks == 1 && h->dim == 3 && getenv("SPK_CUDA_SPLIT_TEST")) {
-    // timing experiment: the boundary / interior launch split of the multi-GPU schedule on one GPU
-    const int32_t lo_box[6] = {0, h->g.gX, 0, h->g.gY, 0, 1};
-    const int32_t hi_box[6] = {0, h->g.gX, 0, h->g.gY, h->nslab - 1, h->nslab};
-    const int32_t in_box[6] = {0, h->g.gX, 0, h->g.gY, 1, h->nslab - 1};
-    for (int s = 0; s < nsweeps; s++) {
-      h->ev.sweep = first_sweep + (uint32_t)s;
-      for (int color = 1; color <= h->nc; color++) {
-        int rc = sweep_set(h, RNG_PHILOX, color, lo_box, 1);
-        if (!rc) rc = sweep_set(h, RNG_PHILOX, color, hi_box, 1);
-        if (!rc) rc = sweep_set(h, RNG_PHILOX, color, in_box, 1);
-        if (rc) return rc;
-      }
-    }
-    return 0;
-  }
   for (int s = 0; s < nsweeps; s++) {
     h->ev.sweep = first_sweep + (uint32_t)s;
     if (fused2d) {
