@@ -41,7 +41,8 @@ def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     cases = [("potts", "sc/26n", (8, 6, 12), 5, 0.7), ("ising", "sq/4n", (10, 16, 1), 2, 1.2),
-             ("potts/neighonly", "tri", (6, 8, 1), 4, 0.5)]
+             ("potts/neighonly", "tri", (6, 8, 1), 4, 0.5), ("potts/neigh", "sc/26n", (6, 6, 8), 4, 0.6),
+             ("ising/single", "sc/6n", (6, 4, 8), 2, 2.0)]
     for model, lat, n, q, T in cases:
         o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
         rng = np.random.default_rng(3)
