@@ -1280,6 +1280,7 @@ int spk_cuda_launch_count(spk_cuda_handle *h, int64_t *launches) {
 int spk_cuda_device_spins(spk_cuda_handle *h, void **dptr) {
   if (!h || !dptr) return fail("null argument");
   *dptr = h->spin;
+  h->ghosts_valid = false;  // the caller may write through the pointer: re-seed the ghosts at the next sweep
   return 0;
 }
 
