@@ -1,0 +1,60 @@
+"""BASELINE.json's full single-GPU sizes, checked through size-independent properties (the oracle
+cannot follow at these sizes): T = 0 dynamics never raise the energy, a uniform lattice is a fixed
+point, counters account for every site, equal seeds give equal runs, cluster volumes partition the
+lattice."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_gb():
+    import torch
+    return torch.cuda.mem_get_info()[0] / 2 ** 30
+
+
+@pytest.mark.parametrize("model,lat,n,q", [
+    ("ising", "sq/4n", (16384, 16384, 1), 2),            # configs[1]
+    ("potts/neighonly", "sc/26n", (1024, 1024, 1024), 10000),  # configs[2]
+    ("potts", "tri", (32768, 16384, 1), 1000),           # configs[4]
+], ids=["ising-16384sq", "neighonly-1024cube", "potts-tri-32768"])
+def test_zero_temperature_properties_at_full_size(model, lat, n, q):
+    from spparks_b200 import LatticeSweep
+    if _free_gb() < 40:
+        pytest.skip("needs 40 GB of free device memory")
+    s = LatticeSweep(model, lat, n[0], n[1], n[2], nspins=q, temperature=0.0, seed=2026)
+    N = s.nlocal
+    s.randomize(7, 1, 2 if model == "ising" else q)
+    e = [s.energy()]
+    for sw in range(3):
+        s.sweeps(sw, 1)
+        e.append(s.energy())
+    assert all(b <= a for a, b in zip(e, e[1:])), e          # T = 0: no event may raise the energy
+    assert e[-1] < e[0]
+    nacc, natt = s.counters()
+    assert natt == 3 * N and 0 < nacc <= natt
+    # the same seed and start give the same run
+    t = LatticeSweep(model, lat, n[0], n[1], n[2], nspins=q, temperature=0.0, seed=2026)
+    t.randomize(7, 1, 2 if model == "ising" else q)
+    t.sweeps(0, 3)
+    assert t.energy() == e[-1] and t.counters() == (nacc, natt)
+    t.close()
+    # cluster volumes partition the lattice
+    nc, mv, mr = s.cluster_stats()
+    assert 1 <= nc <= N and mv == N / nc and mr > 0
+    s.close()
+
+
+def test_uniform_lattice_is_a_fixed_point_at_full_size():
+    """every neighbour equal: ising/potts at T = 0 reject every change, potts/neighonly has no event."""
+    from spparks_b200 import LatticeSweep
+    if _free_gb() < 20:
+        pytest.skip("needs 20 GB of free device memory")
+    L = 1024
+    for model in ("potts/neighonly", "potts/pin"):
+        s = LatticeSweep(model, "sc/26n", L, L, L, nspins=10000, temperature=0.0, seed=1)
+        s.randomize(3, 77, 77)  # every site 77
+        s.sweeps(0, 2)
+        assert s.energy() == 0.0 and s.counters() == (0, 2 * L ** 3)
+        assert s.cluster_stats()[0] == 1
+        s.close()
