@@ -1,0 +1,87 @@
+// Internal: the handle behind the C ABI and the helpers every translation unit of the library shares.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nccl.h>  // types only: the library is bound lazily with dlopen (spk_cuda.cu: NcclApi)
+
+#include <cstdint>
+#include <utility>
+
+#include "../../include/spparks_cuda.h"
+#include "sweep_generic.cuh"
+
+// formats the thread's last-error string (spk_cuda_last_error) and returns 1
+int spk_fail(const char *fmt, ...);
+#define fail spk_fail
+
+#define CU(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+using namespace spk;
+
+struct spk_cuda_handle {
+  spk_cuda_desc d;
+  int dim, nb, nn, nc;
+  Geo g;
+  int64_t nlocal, nglobal, plane;  // plane = elements of one plane (3-D) / row (2-D) of the slab dimension
+  int nslab;                       // local extent along the slab dimension
+  int gh = 1;                      // ghost planes / rows on each side of the slab
+  bool fused2d_ok = false;         // colour-fused 2-D tile kernel usable (tensor map built)
+  bool use_fused = true;           // SPK_CUDA_NO_FUSED=1 keeps the per-colour kernels (A/B tests)
+  int32_t *base = nullptr;         // allocation incl. ghost planes
+  int32_t *spin = nullptr;         // first owned site
+  double *u1 = nullptr, *u2 = nullptr;
+  int32_t *seeds = nullptr;
+  unsigned long long *naccept = nullptr, *escratch = nullptr;
+  int64_t nattempt = 0, launches = 0;
+  EventParams ev;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr, ev_halo = nullptr, ev_compute = nullptr;
+  ncclComm_t comm = nullptr;
+  bool tiled = true;  // tuned kernels allowed (SPK_CUDA_FORCE_GENERIC=1 disables, for A/B tests)
+  bool use_stream = true;  // SPK_CUDA_NO_STREAM=1 keeps the strip kernel (A/B tests)
+  bool smem_attr_set[9] = {false, false, false, false, false, false, false, false, false};  // dynamic shared memory opt-in done: [0] tile2d, [1..8] stream variants
+  uint32_t *cl_label = nullptr, *cl_size = nullptr;  // diag_style cluster: union-find parents, volumes / ids per root
+  uint32_t *cl_blocksum = nullptr;
+  unsigned long long *cl_count = nullptr;             // [0] ncluster, [1] (as double) sum of radii
+  int32_t *edge = nullptr;     // tile-edge words of the colour-pair launches (StreamMap::edge)
+  size_t edge_words = 0;
+  bool use_pair = false;       // SPK_CUDA_PAIR=1: sc/26n colour pairs in one launch (half the DRAM traffic; measured slower)
+  bool pk16 = false;       // every spin <= PK16_MAX_SPIN: packed 16-bit compares (SPK_CUDA_NO_PK16=1 disables, for A/B tests)
+  bool stream_ok = false;  // TMA streaming kernel usable (3-D lattice, tensor map built)
+  CUtensorMap tmap;        // (x, y, plane incl. the two ghost planes) view of the slab
+  int32_t *base_alt = nullptr;  // second lattice buffer of the out-of-place fused 2-D sweep
+  CUtensorMap tmap_alt;
+  // peer-memory halo (3-D slabs through the streaming kernel): the boundary launches of a colour
+  // store straight into the ring neighbours' ghost planes over NVLink, ordered by flag words
+  bool p2p = false;
+  void *peer_map[2] = {nullptr, nullptr};       // mapped lattice allocations of the lower / upper neighbour
+  void *peer_map_alt[2] = {nullptr, nullptr};   // ... and of their second buffers (2-D ping-pong)
+  int32_t *alloc0 = nullptr;                    // the allocation `base` pointed to at create (the buffers swap per fused sweep, in lockstep on all ranks)
+  void *peer_flag_map[2] = {nullptr, nullptr};  // mapped flag words of the lower / upper neighbour
+  uint32_t *flags = nullptr;      // [0] boundary steps finished by the lower neighbour, [1] by the upper, [2] wait timed out
+  uint32_t *peer_flags[2] = {nullptr, nullptr};  // the words this rank signals: lower's [1], upper's [0]
+  int32_t *mirror_lo = nullptr, *mirror_hi = nullptr;  // lower neighbour's upper ghost plane, upper neighbour's lower ghost plane
+  bool mirror_active = false;     // boundary launches of spk_cuda_sweeps only
+  bool ghosts_valid = false;      // ghost planes hold the neighbours' current boundary planes
+  uint32_t step = 0;              // boundary steps signalled so far (same sequence on every rank)
+};
+
+namespace spk {
+// sector box (global cells) -> local cell ranges of this slab; false if empty
+bool local_box(const spk_cuda_handle *h, const int32_t *box, Box &b);
+
+// Per-application entry points: each model's kernels are instantiated in their own translation
+// unit (model_*.cu) so that the library builds in parallel.
+template <int MODEL> struct ModelEntry {
+  // one colour set (src/app_lattice.cpp:674-691): tuned kernel where it applies, else generic
+  static int sweep_set(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop);
+  // colour-fused 2-D sweep (launch_tile2d): 0 launched, -1 not applicable, >0 error
+  static int fused(spk_cuda_handle *h, const SweepArgs &a, int part);
+  // sc/26n colour pair: 0 launched, -1 not applicable, >0 error
+  static int pair(spk_cuda_handle *h, int color, const int32_t *box);
+};
+}  // namespace spk

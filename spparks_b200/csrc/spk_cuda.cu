@@ -13,21 +13,17 @@
 #include <utility>
 #include <vector>
 
-#include "../../include/spparks_cuda.h"
+#include "handle.h"
 #include "aux_kernels.cuh"
 #include "cluster.cuh"
-#include "sweep_generic.cuh"
-#include "sweep_stream.cuh"
-#include "sweep_tile2d.cuh"
-#include "sweep_tiled.cuh"
-
-using namespace spk;
+#include "sweep_stream.cuh"   // StreamCfg (tensor-map box shapes)
+#include "sweep_tile2d.cuh"   // Tile2dCfg
 
 namespace {
-
 thread_local std::string g_err;
+}
 
-int fail(const char *fmt, ...) {
+int spk_fail(const char *fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -37,11 +33,17 @@ int fail(const char *fmt, ...) {
   return 1;
 }
 
-#define CU(call)                                                                        \
-  do {                                                                                  \
-    cudaError_t e_ = (call);                                                            \
-    if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-  } while (0)
+namespace spk {
+extern template struct ModelEntry<SPK_ISING>;
+extern template struct ModelEntry<SPK_POTTS>;
+extern template struct ModelEntry<SPK_POTTS_NEIGHONLY>;
+extern template struct ModelEntry<SPK_POTTS_PIN>;
+extern template struct ModelEntry<SPK_ISING_SINGLE>;
+extern template struct ModelEntry<SPK_POTTS_NEIGH>;
+}  // namespace spk
+
+namespace {
+
 // NCCL is bound at the first multi-GPU call, not at link time: a host process (PyTorch, an MPI
 // SPPARKS) may already carry its own libnccl.so.2 and two copies must not be mixed.  dlopen by
 // SONAME returns the copy that is already loaded, if any.  SPK_CUDA_NCCL_LIB overrides the path.
@@ -83,53 +85,6 @@ int lat_dim(int lat) { return (lat == SPK_SC_6N || lat == SPK_SC_26N) ? 3 : 2; }
 
 }  // namespace
 
-struct spk_cuda_handle {
-  spk_cuda_desc d;
-  int dim, nb, nn, nc;
-  Geo g;
-  int64_t nlocal, nglobal, plane;  // plane = elements of one plane (3-D) / row (2-D) of the slab dimension
-  int nslab;                       // local extent along the slab dimension
-  int gh = 1;                      // ghost planes / rows on each side of the slab
-  bool fused2d_ok = false;         // colour-fused 2-D tile kernel usable (tensor map built)
-  bool use_fused = true;           // SPK_CUDA_NO_FUSED=1 keeps the per-colour kernels (A/B tests)
-  int32_t *base = nullptr;         // allocation incl. ghost planes
-  int32_t *spin = nullptr;         // first owned site
-  double *u1 = nullptr, *u2 = nullptr;
-  int32_t *seeds = nullptr;
-  unsigned long long *naccept = nullptr, *escratch = nullptr;
-  int64_t nattempt = 0, launches = 0;
-  EventParams ev;
-  cudaStream_t stream = nullptr, comm_stream = nullptr;
-  cudaEvent_t t0 = nullptr, t1 = nullptr, ev_halo = nullptr, ev_compute = nullptr;
-  ncclComm_t comm = nullptr;
-  bool tiled = true;  // tuned kernels allowed (SPK_CUDA_FORCE_GENERIC=1 disables, for A/B tests)
-  bool use_stream = true;  // SPK_CUDA_NO_STREAM=1 keeps the strip kernel (A/B tests)
-  bool smem_attr_set[9] = {false, false, false, false, false, false, false, false, false};  // dynamic shared memory opt-in done: [0] tile2d, [1..8] stream variants
-  uint32_t *cl_label = nullptr, *cl_size = nullptr;  // diag_style cluster: union-find parents, volumes / ids per root
-  uint32_t *cl_blocksum = nullptr;
-  unsigned long long *cl_count = nullptr;             // [0] ncluster, [1] (as double) sum of radii
-  int32_t *edge = nullptr;     // tile-edge words of the colour-pair launches (StreamMap::edge)
-  size_t edge_words = 0;
-  bool use_pair = false;       // SPK_CUDA_PAIR=1: sc/26n colour pairs in one launch (half the DRAM traffic; measured slower)
-  bool pk16 = false;       // every spin <= PK16_MAX_SPIN: packed 16-bit compares (SPK_CUDA_NO_PK16=1 disables, for A/B tests)
-  bool stream_ok = false;  // TMA streaming kernel usable (3-D lattice, tensor map built)
-  CUtensorMap tmap;        // (x, y, plane incl. the two ghost planes) view of the slab
-  int32_t *base_alt = nullptr;  // second lattice buffer of the out-of-place fused 2-D sweep
-  CUtensorMap tmap_alt;
-  // peer-memory halo (3-D slabs through the streaming kernel): the boundary launches of a colour
-  // store straight into the ring neighbours' ghost planes over NVLink, ordered by flag words
-  bool p2p = false;
-  void *peer_map[2] = {nullptr, nullptr};       // mapped lattice allocations of the lower / upper neighbour
-  void *peer_map_alt[2] = {nullptr, nullptr};   // ... and of their second buffers (2-D ping-pong)
-  int32_t *alloc0 = nullptr;                    // the allocation `base` pointed to at create (the buffers swap per fused sweep, in lockstep on all ranks)
-  void *peer_flag_map[2] = {nullptr, nullptr};  // mapped flag words of the lower / upper neighbour
-  uint32_t *flags = nullptr;      // [0] boundary steps finished by the lower neighbour, [1] by the upper, [2] wait timed out
-  uint32_t *peer_flags[2] = {nullptr, nullptr};  // the words this rank signals: lower's [1], upper's [0]
-  int32_t *mirror_lo = nullptr, *mirror_hi = nullptr;  // lower neighbour's upper ghost plane, upper neighbour's lower ghost plane
-  bool mirror_active = false;     // boundary launches of spk_cuda_sweeps only
-  bool ghosts_valid = false;      // ghost planes hold the neighbours' current boundary planes
-  uint32_t step = 0;              // boundary steps signalled so far (same sequence on every rank)
-};
 
 namespace {
 
@@ -159,8 +114,10 @@ void build_tables(spk_cuda_handle *h) {
   }
 }
 
+}  // namespace
+
 // sector box (global cells) -> local cell ranges of this slab; false if empty
-bool local_box(const spk_cuda_handle *h, const int32_t *box, Box &b) {
+bool spk::local_box(const spk_cuda_handle *h, const int32_t *box, Box &b) {
   const Geo &g = h->g;
   int lo[3] = {0, 0, 0}, hi[3] = {g.gX, g.gY, g.gZ};
   if (box)
@@ -176,46 +133,8 @@ bool local_box(const spk_cuda_handle *h, const int32_t *box, Box &b) {
   return lo[0] < hi[0] && lo[1] < hi[1] && lo[2] < hi[2];
 }
 
-// sites of colour c0 inside the local box (nattempt += nselect, src/app_lattice.cpp:677)
-template <int LAT> int64_t class_count(const spk_cuda_handle *h, const Box &b, int c0) {
-  auto par = [](int lo, int hi, int p) -> int64_t {  // # of x in [lo,hi) with x%2 == p
-    int first = lo + ((lo ^ p) & 1);
-    return first < hi ? (hi - first + 1) / 2 : 0;
-  };
-  const int64_t ni = b.ihi - b.ilo, nj = b.jhi - b.jlo, nk = b.khi - b.klo;
-  if (LAT == SPK_SQ_4N || LAT == SPK_SC_6N) {
-    int64_t n = 0;
-    for (int k = b.klo; k < b.khi; k++)
-      for (int par_j = 0; par_j < 2; par_j++) {
-        int shift = LAT == SPK_SQ_4N ? h->g.g0 : k + h->g.g0;
-        n += par(b.jlo, b.jhi, par_j) * par(b.ilo, b.ihi, (c0 + par_j + shift) & 1);
-      }
-    return n;
-  }
-  if (LAT == SPK_SQ_8N) return par(b.ilo, b.ihi, c0 & 1) * par(b.jlo, b.jhi, (c0 >> 1) & 1);
-  if (LAT == SPK_TRI) return par(b.ilo, b.ihi, (c0 >> 1) & 1) * nj;
-  (void)ni; (void)nk;
-  return par(b.ilo, b.ihi, c0 & 1) * par(b.jlo, b.jhi, (c0 >> 1) & 1) * par(b.klo, b.khi, (c0 >> 2) & 1);
-}
+namespace {
 
-template <int LAT, int MODEL, int RNG>
-int launch_generic(spk_cuda_handle *h, const SweepArgs &a) {
-  const Box &b = a.b;
-  const int half_x = (b.ihi - b.ilo + 1) / 2 + 1;
-  int rows = b.jhi - b.jlo, planes = b.khi - b.klo;
-  if (LAT == SPK_SQ_8N || LAT == SPK_SC_26N) rows = rows / 2 + 1;
-  if (LAT == SPK_SC_26N) planes = planes / 2 + 1;
-  if (Lat<LAT>::DIM == 2) planes = 1;
-  dim3 block(64, 4, 1);
-  dim3 grid((half_x + 63) / 64, (rows + 3) / 4, planes);
-  if (grid.y > 65535 || grid.z > 65535) return fail("lattice too large for the generic kernel grid");
-  sweep_generic_kernel<LAT, MODEL, RNG><<<grid, block, 0, h->stream>>>(a);
-  h->launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-// TMA descriptor of the slab: int32 tensor (x, y, plane) whose plane 0 is the lower ghost plane.
 // cuTensorMapEncodeTiled is fetched through the runtime so that libcuda is not a link dependency.
 int build_tensor_map(spk_cuda_handle *h) {
   h->stream_ok = false;
@@ -292,68 +211,17 @@ int refresh_ghosts_local(spk_cuda_handle *h) {
   return 0;
 }
 
-// whole colour-fused sweep of a 2-D lattice; returns 0 launched, -1 not applicable, >0 error
-// part: 0 = every tile row and swap the buffers; 1 = first and last tile row only (the rows the
-// neighbours' ghost rows depend on); 2 = the tile rows in between, then swap the buffers
-template <int LAT, int MODEL>
-int launch_tile2d(spk_cuda_handle *h, const SweepArgs &a, int part) {
-  if constexpr (Lat<LAT>::DIM != 2) {
-    return -1;
-  } else {
-    using C = Tile2dCfg<LAT>;
-    if (!h->fused2d_ok) return -1;
-    const int rowlen = h->g.X * Lat<LAT>::NB;
-    Tile2dMap tm;
-    tm.ntx = (rowlen + C::OW - 1) / C::OW;
-    tm.nty = (h->nslab + T2_OH - 1) / T2_OH;
-    tm.gh = h->gh;
-    tm.ty0 = 0; tm.ty_run = tm.nty; tm.ty_alt = -1;
-    if (part == 1) { tm.ty_run = tm.nty > 1 ? 2 : 1; tm.ty_alt = tm.nty > 1 ? tm.nty - 1 : -1; }
-    if (part == 2) { tm.ty0 = 1; tm.ty_run = tm.nty - 2; }
-    tm.items = tm.ntx * tm.ty_run;
-    const bool swap_after = part != 1;
-    if (tm.ty_run <= 0) {
-      if (swap_after) {
-        std::swap(h->base, h->base_alt);
-        std::swap(h->tmap, h->tmap_alt);
-        h->spin = h->base + (int64_t)h->gh * h->plane;
-      }
-      return 0;
-    }
-    if (!h->smem_attr_set[0]) {  // per handle: the attribute belongs to the device the handle lives on
-      if (cudaFuncSetAttribute(sweep_tile2d_kernel<LAT, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               C::SMEM_BYTES) != cudaSuccess)
-        return 1;
-      h->smem_attr_set[0] = true;
-    }
-    const int grid_max = 3 * 148;
-    const int grid = tm.items < grid_max ? tm.items : grid_max;
-    int32_t *dst = h->base_alt + (int64_t)h->gh * h->plane;
-    sweep_tile2d_kernel<LAT, MODEL><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, a, tm, dst);
-    h->launches++;
-    if (cudaGetLastError() != cudaSuccess) return 1;
-    if (swap_after) {  // the destination becomes the lattice (stream order makes this safe for later launches)
-      std::swap(h->base, h->base_alt);
-      std::swap(h->tmap, h->tmap_alt);
-      h->spin = h->base + (int64_t)h->gh * h->plane;
-    }
-    return 0;
-  }
-}
-
-template <int LAT> int fused_sweep_l(spk_cuda_handle *h, const SweepArgs &a, int part) {
+int fused_sweep_m(spk_cuda_handle *h, const SweepArgs &a, int part) {
   switch (h->d.model) {
-    case SPK_ISING: return launch_tile2d<LAT, SPK_ISING>(h, a, part);
-    case SPK_POTTS: return launch_tile2d<LAT, SPK_POTTS>(h, a, part);
-    case SPK_POTTS_NEIGHONLY: return launch_tile2d<LAT, SPK_POTTS_NEIGHONLY>(h, a, part);
-    case SPK_POTTS_PIN: return launch_tile2d<LAT, SPK_POTTS_PIN>(h, a, part);
-    case SPK_ISING_SINGLE: return launch_tile2d<LAT, SPK_ISING_SINGLE>(h, a, part);
-    case SPK_POTTS_NEIGH: return launch_tile2d<LAT, SPK_POTTS_NEIGH>(h, a, part);
+    case SPK_ISING: return ModelEntry<SPK_ISING>::fused(h, a, part);
+    case SPK_POTTS: return ModelEntry<SPK_POTTS>::fused(h, a, part);
+    case SPK_POTTS_NEIGHONLY: return ModelEntry<SPK_POTTS_NEIGHONLY>::fused(h, a, part);
+    case SPK_POTTS_PIN: return ModelEntry<SPK_POTTS_PIN>::fused(h, a, part);
+    case SPK_ISING_SINGLE: return ModelEntry<SPK_ISING_SINGLE>::fused(h, a, part);
+    case SPK_POTTS_NEIGH: return ModelEntry<SPK_POTTS_NEIGH>::fused(h, a, part);
   }
   return -1;
 }
-
-// one whole sweep (all colours) by the fused 2-D kernel (part: see launch_tile2d): 0 done,
 // -1 not applicable, >0 error.  On one GPU the ghost rows are refreshed here.
 int fused_sweep(spk_cuda_handle *h, int part) {
   if (!h->tiled || !h->use_fused || h->dim != 2 || !h->fused2d_ok) return -1;
@@ -363,162 +231,33 @@ int fused_sweep(spk_cuda_handle *h, int part) {
   a.mirror_lo = a.mirror_hi = nullptr;
   a.b = Box{0, h->g.X, 0, h->g.Y, 0, 1};
   if (h->d.nranks == 1 && refresh_ghosts_local(h)) return 1;
-  int rc;
-  switch (h->d.lattice) {
-    case SPK_SQ_4N: rc = fused_sweep_l<SPK_SQ_4N>(h, a, part); break;
-    case SPK_SQ_8N: rc = fused_sweep_l<SPK_SQ_8N>(h, a, part); break;
-    case SPK_TRI: rc = fused_sweep_l<SPK_TRI>(h, a, part); break;
-    default: rc = -1;
-  }
+  const int rc = fused_sweep_m(h, a, part);
   if (rc == 0 && part != 1) h->nattempt += h->nlocal;
   return rc;
 }
 
-// returns 0 launched, -1 not applicable, >0 error
-// pair: colours c0 (even) and c0 + 1 of sc/26n in ONE launch (sweep_stream.cuh: stream_chunk_pair)
-template <int LAT, int MODEL>
-int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
-  if constexpr (LAT != SPK_SC_26N && LAT != SPK_SC_6N) {
-    return -1;
-  } else {
-    if (pair && (LAT != SPK_SC_26N || ising_like(MODEL) || (a.c0 & 1) || a.nloop != 1)) return -1;
-    using C = StreamCfg<LAT>;
-    const Geo &g = a.g;
-    const Box &b = a.b;
-    if (!h->stream_ok || b.ilo != 0 || b.ihi != g.X || b.jlo != 0 || b.jhi != g.Y) return -1;
-    StreamMap sm;
-    sm.edge = nullptr;
-    sm.nrows = 0;
-    const int c0 = a.c0;
-    int kfirst = b.klo, nq = b.khi - b.klo;
-    if (LAT == SPK_SC_26N) {
-      kfirst = b.klo + ((b.klo ^ (c0 >> 2)) & 1);
-      nq = kfirst < b.khi ? (b.khi - kfirst + 1) / 2 : 0;
-    }
-    if (nq <= 0) return 0;
-    sm.ntx = (g.X + ST_TX - 1) / ST_TX;
-    sm.nty = (g.Y + C::YT - 1) / C::YT;
-    sm.kfirst = kfirst;
-    sm.nq = nq;
-    const int grid_max = 2 * 148;
-    // work items per resident CTA (plane chunks are cut so that there are about this many): more
-    // items balance the tail better, fewer re-read fewer chunk-boundary planes (SPK_CUDA_ITEMS_PER_CTA, A/B tests)
-    static const int items_per_cta = [] { const char *e = getenv("SPK_CUDA_ITEMS_PER_CTA"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
-    int nzc = (items_per_cta * grid_max + sm.ntx * sm.nty - 1) / (sm.ntx * sm.nty);
-    if (nzc > nq) nzc = nq;
-    if (nzc < 1) nzc = 1;
-    sm.qchunk = (nq + nzc - 1) / nzc;
-    sm.nzc = (nq + sm.qchunk - 1) / sm.qchunk;
-    sm.items = sm.ntx * sm.nty * sm.nzc;
-    const int grid = sm.items < grid_max ? sm.items : grid_max;
-    SweepArgs args = a;  // Geo::lo_wrap / hi_wrap select periodic images (1 GPU) or ghost planes (slabs)
-    // P16: packed 16-bit compares (event.cuh) when every spin fits; the Ising shortcut has no compares to pack
-    auto launch = [&](auto ONE, auto PK, auto PAIR) -> int {
-      constexpr bool one = decltype(ONE)::value, pk = decltype(PK)::value && !ising_like(MODEL);
-      constexpr bool pr = decltype(PAIR)::value && one && LAT == SPK_SC_26N && !ising_like(MODEL);
-      if constexpr (pr) {  // tile-edge words first (stream order: they see the lattice before the pair launch)
-        sm.nrows = g.Y / 2;
-        const size_t words = 2 * (size_t)sm.ntx * sm.nrows * sm.nq;
-        const size_t words_max = 2 * (size_t)sm.ntx * sm.nrows * ((h->nslab + 1) / 2);  // whole-slab launch: allocate once
-        if (words > h->edge_words) {
-          cudaFree(h->edge);
-          h->edge = nullptr;
-          h->edge_words = 0;
-          if (cudaMalloc(&h->edge, words_max * sizeof(int32_t)) != cudaSuccess) return 1;
-          h->edge_words = words_max;
-        }
-        sm.edge = h->edge;
-        const long long total = (long long)(words / 2);
-        edge_pair_kernel<MODEL, pk><<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(args, sm, h->edge);
-        h->launches++;
-      }
-      auto *kern = sweep_stream_kernel<LAT, MODEL, one, pk, pr>;
-      bool &attr = h->smem_attr_set[1 + (one ? 0 : 1) + (pk ? 2 : 0) + (pr ? 4 : 0)];
-      if (!attr) {  // per handle: the attribute belongs to the device the handle lives on
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) return 1;
-        attr = true;
-      }
-      kern<<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, args, sm);
-      return 0;
-    };
-    using T = std::true_type;
-    using F = std::false_type;
-    int rc;
-    if (pair) rc = h->pk16 ? launch(T{}, T{}, T{}) : launch(T{}, F{}, T{});
-    else if (args.nloop == 1) rc = h->pk16 ? launch(T{}, T{}, F{}) : launch(T{}, F{}, F{});
-    else rc = h->pk16 ? launch(F{}, T{}, F{}) : launch(F{}, F{}, F{});
-    if (rc) return rc;
-    h->launches++;
-    return cudaGetLastError() == cudaSuccess ? 0 : 1;
-  }
-}
-
-template <int LAT, int MODEL>
-int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
-  SweepArgs a;
-  a.spin = h->spin; a.g = h->g; a.c0 = color - 1; a.nloop = nloop; a.ev = h->ev;
-  a.u1 = h->u1; a.u2 = h->u2; a.seeds = h->seeds; a.naccept = h->naccept;
-  a.mirror_lo = h->mirror_active ? h->mirror_lo : nullptr;
-  a.mirror_hi = h->mirror_active ? h->mirror_hi : nullptr;
-  if (!local_box(h, box, a.b)) return 0;
-  h->nattempt += class_count<LAT>(h, a.b, a.c0) * nloop;
-  if (rng == RNG_PHILOX) {
-    if (h->tiled) {
-      int rc = h->use_stream ? launch_stream<LAT, MODEL>(h, a) : -1;
-      if (rc == 0) return 0;
-      if (rc > 0) return fail("stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-      if (h->mirror_active) return fail("peer-memory halo needs the streaming kernel");
-      rc = launch_tiled<LAT, MODEL>(h->stream, a, &h->launches);
-      if (rc == 0) return 0;
-      if (rc > 0) return fail("tiled kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    return launch_generic<LAT, MODEL, RNG_PHILOX>(h, a);
-  }
-  if (rng == RNG_INJECTED) return launch_generic<LAT, MODEL, RNG_INJECTED>(h, a);
-  return launch_generic<LAT, MODEL, RNG_STRICT>(h, a);
-}
-
-// colours `color` (odd, 1-based) and color + 1 of sc/26n as one launch: 0 launched, -1 not applicable
-template <int MODEL> int sweep_pair_m(spk_cuda_handle *h, int color, const int32_t *box) {
-  SweepArgs a;
-  a.spin = h->spin; a.g = h->g; a.c0 = color - 1; a.nloop = 1; a.ev = h->ev;
-  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept;
-  a.mirror_lo = h->mirror_active ? h->mirror_lo : nullptr;
-  a.mirror_hi = h->mirror_active ? h->mirror_hi : nullptr;
-  if (!local_box(h, box, a.b)) return 0;
-  const int rc = launch_stream<SPK_SC_26N, MODEL>(h, a, true);
-  if (rc == 0) h->nattempt += class_count<SPK_SC_26N>(h, a.b, a.c0) + class_count<SPK_SC_26N>(h, a.b, a.c0 + 1);
-  return rc;
-}
 
 bool pair_ok(const spk_cuda_handle *h) {
   return h->use_pair && h->tiled && h->use_stream && h->stream_ok && h->d.lattice == SPK_SC_26N && !ising_like(h->d.model);
 }
 
-int sweep_pair(spk_cuda_handle *h, int color, const int32_t *box) {
-  int rc = -1;
+int sweep_pair_m(spk_cuda_handle *h, int color, const int32_t *box) {
   switch (h->d.model) {
-    case SPK_POTTS: rc = sweep_pair_m<SPK_POTTS>(h, color, box); break;
-    case SPK_POTTS_NEIGHONLY: rc = sweep_pair_m<SPK_POTTS_NEIGHONLY>(h, color, box); break;
-    case SPK_POTTS_PIN: rc = sweep_pair_m<SPK_POTTS_PIN>(h, color, box); break;
-    case SPK_POTTS_NEIGH: rc = sweep_pair_m<SPK_POTTS_NEIGH>(h, color, box); break;
-    default: break;
+    case SPK_ISING: return ModelEntry<SPK_ISING>::pair(h, color, box);
+    case SPK_POTTS: return ModelEntry<SPK_POTTS>::pair(h, color, box);
+    case SPK_POTTS_NEIGHONLY: return ModelEntry<SPK_POTTS_NEIGHONLY>::pair(h, color, box);
+    case SPK_POTTS_PIN: return ModelEntry<SPK_POTTS_PIN>::pair(h, color, box);
+    case SPK_ISING_SINGLE: return ModelEntry<SPK_ISING_SINGLE>::pair(h, color, box);
+    case SPK_POTTS_NEIGH: return ModelEntry<SPK_POTTS_NEIGH>::pair(h, color, box);
   }
+  return -1;
+}
+
+int sweep_pair(spk_cuda_handle *h, int color, const int32_t *box) {
+  const int rc = sweep_pair_m(h, color, box);
   if (rc > 0) return fail("colour-pair launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (rc < 0) return fail("colour-pair launch not applicable");
   return 0;
-}
-
-template <int LAT> int sweep_set_l(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
-  switch (h->d.model) {
-    case SPK_ISING: return sweep_set_lm<LAT, SPK_ISING>(h, rng, color, box, nloop);
-    case SPK_POTTS: return sweep_set_lm<LAT, SPK_POTTS>(h, rng, color, box, nloop);
-    case SPK_POTTS_NEIGHONLY: return sweep_set_lm<LAT, SPK_POTTS_NEIGHONLY>(h, rng, color, box, nloop);
-    case SPK_POTTS_PIN: return sweep_set_lm<LAT, SPK_POTTS_PIN>(h, rng, color, box, nloop);
-    case SPK_ISING_SINGLE: return sweep_set_lm<LAT, SPK_ISING_SINGLE>(h, rng, color, box, nloop);
-    case SPK_POTTS_NEIGH: return sweep_set_lm<LAT, SPK_POTTS_NEIGH>(h, rng, color, box, nloop);
-  }
-  return fail("unknown model %d", h->d.model);
 }
 
 int sweep_set(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
@@ -527,14 +266,15 @@ int sweep_set(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nl
   if (color < 1 || color > h->nc) return fail("colour %d out of range 1..%d", color, h->nc);
   if (nloop < 1) return fail("nloop must be >= 1");
   CU(cudaSetDevice(h->d.device));
-  switch (h->d.lattice) {
-    case SPK_SQ_4N: return sweep_set_l<SPK_SQ_4N>(h, rng, color, box, nloop);
-    case SPK_SQ_8N: return sweep_set_l<SPK_SQ_8N>(h, rng, color, box, nloop);
-    case SPK_TRI: return sweep_set_l<SPK_TRI>(h, rng, color, box, nloop);
-    case SPK_SC_6N: return sweep_set_l<SPK_SC_6N>(h, rng, color, box, nloop);
-    case SPK_SC_26N: return sweep_set_l<SPK_SC_26N>(h, rng, color, box, nloop);
+  switch (h->d.model) {
+    case SPK_ISING: return ModelEntry<SPK_ISING>::sweep_set(h, rng, color, box, nloop);
+    case SPK_POTTS: return ModelEntry<SPK_POTTS>::sweep_set(h, rng, color, box, nloop);
+    case SPK_POTTS_NEIGHONLY: return ModelEntry<SPK_POTTS_NEIGHONLY>::sweep_set(h, rng, color, box, nloop);
+    case SPK_POTTS_PIN: return ModelEntry<SPK_POTTS_PIN>::sweep_set(h, rng, color, box, nloop);
+    case SPK_ISING_SINGLE: return ModelEntry<SPK_ISING_SINGLE>::sweep_set(h, rng, color, box, nloop);
+    case SPK_POTTS_NEIGH: return ModelEntry<SPK_POTTS_NEIGH>::sweep_set(h, rng, color, box, nloop);
   }
-  return fail("unknown lattice %d", h->d.lattice);
+  return fail("unknown model %d", h->d.model);
 }
 
 }  // namespace
