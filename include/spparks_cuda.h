@@ -111,6 +111,15 @@ int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps);
 int spk_cuda_counters(spk_cuda_handle *h, int64_t *naccept, int64_t *nattempt);
 int spk_cuda_reset_counters(spk_cuda_handle *h);
 
+/* Candidate-list apps (potts/neighonly, potts/neigh) on sc/26n: which of the two equivalent
+ * first-occurrence algorithms (src/app_potts_neighonly.cpp:81-88) the colour kernels currently use:
+ * 0 = all-pairs chain (cost independent of the spins), 1 = candidate elimination (cost
+ * proportional to the distinct neighbour values; the production path once grains have formed),
+ * -1 = not applicable to this handle.  mean_distinct (may be NULL) receives the last mean number
+ * of candidates per attempted site the kernels reported, or -1.  The library switches by itself
+ * (SPK_CUDA_NEIGH_MODE=chain|adaptive|auto, default auto); results are bit-identical either way. */
+int spk_cuda_neigh_variant(spk_cuda_handle *h, int *variant, double *mean_distinct);
+
 /* diag_style energy (src/diag_energy.cpp:53-66): sum of site_energy over owned sites */
 int spk_cuda_energy(spk_cuda_handle *h, double *energy);
 

@@ -24,7 +24,7 @@ SYMBOLS = [
     "spk_cuda_counters", "spk_cuda_reset_counters", "spk_cuda_energy", "spk_cuda_comm_id",
     "spk_cuda_comm_init", "spk_cuda_halo_exchange", "spk_cuda_halo_mode", "spk_cuda_sync", "spk_cuda_timer_start",
     "spk_cuda_timer_stop", "spk_cuda_launch_count", "spk_cuda_device_spins", "spk_cuda_cluster_stats",
-    "spk_cuda_cluster_ids",
+    "spk_cuda_cluster_ids", "spk_cuda_neigh_variant",
 ]
 
 
@@ -80,6 +80,7 @@ def load():
     L.spk_cuda_halo_mode.argtypes = [vp]
     L.spk_cuda_cluster_stats.argtypes = [vp, i64p, dp, dp]
     L.spk_cuda_cluster_ids.argtypes = [vp, i32p, i64p, C.c_int64]
+    L.spk_cuda_neigh_variant.argtypes = [vp, C.POINTER(C.c_int), dp]
     L.spk_cuda_sync.argtypes = [vp]
     L.spk_cuda_timer_start.argtypes = [vp]
     L.spk_cuda_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]

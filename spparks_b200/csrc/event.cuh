@@ -218,11 +218,138 @@ template <int NN> __device__ __forceinline__ int select_slot(const int (&v)[NN],
   return t[0];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Candidate elimination for the candidate-list apps on sc/26n (packed 16-bit spins): work
+// proportional to the number of DISTINCT neighbour values instead of the 351 pairwise tests of
+// first_occurrence_mask16.  After a few sweeps of grain growth a site sees 2-6 distinct values
+// (a fresh random lattice: 26), so this is the production path once the lattice has coarsened;
+// the host picks the variant per launch from a device-side statistic (spk_cuda.cu: neigh_mode).
+//
+// Layout: word j (0..12) holds the negated pair (slot j, slot j+13), so that in a result mask
+// bit j <-> slot j and bit 16+j <-> slot 13+j: bit order = reference neighbour order, the lowest
+// set bit of a mask is its earliest slot.
+constexpr uint32_t NB26_VALID = 0x1FFF1FFFu;
+__host__ __device__ constexpr int nb26_bit_to_slot(int b) { return b < 16 ? b : b - 3; }
+
+// bit set <=> that slot's value differs from c  (13 VIADDMNMX on the ALU pipe + 13 IMAD gathers
+// on the FMA pipe)
+__device__ __forceinline__ uint32_t nb26_gather(const uint32_t (&t)[13], const EventParams &p) {
+  uint32_t s[2];
+#pragma unroll
+  for (int j = 0; j < 13; j++) {
+    if (j == 0) s[0] = t[0];
+    else if (j == 1) s[1] = t[1] * p.pow2[1];
+    else s[j & 1] = t[j] * p.pow2[j] + s[j & 1];
+  }
+  return s[1] * (uint32_t)p.one + s[0];
+}
+__device__ __forceinline__ uint32_t nb26_unequal_mask(const uint32_t (&w)[13], int c, const EventParams &p) {
+  const uint32_t a = pk_rep(c, p);
+  uint32_t t[13];
+#pragma unroll
+  for (int j = 0; j < 13; j++) t[j] = __viaddmin_u16x2(a, w[j], 0x00010001u);
+  return nb26_gather(t, p);
+}
+// bit set <=> that slot's value differs from c1 AND from c2: the second test takes the first
+// one's result as its min operand, so two candidates share one gather
+__device__ __forceinline__ uint32_t nb26_unequal_mask2(const uint32_t (&w)[13], int c1, int c2, const EventParams &p) {
+  const uint32_t a1 = pk_rep(c1, p), a2 = pk_rep(c2, p);
+  uint32_t t[13];
+#pragma unroll
+  for (int j = 0; j < 13; j++) t[j] = __viaddmin_u16x2(a2, w[j], __viaddmin_u16x2(a1, w[j], 0x00010001u));
+  return nb26_gather(t, p);
+}
+
+// site_event_rejection of potts/neighonly (src/app_potts_neighonly.cpp:71-117) and potts/neigh
+// (src/app_potts_neigh.cpp:71-116) by candidate elimination, for the TWO class sites of a chunk at
+// once (two independent dependency chains per thread hide the latency of a pass).
+// fetch(h, b) returns the neighbour value of site h behind mask bit b (the streaming kernel reads
+// it from the shared-memory planes; bit 31 is never a neighbour and must return any valid spin).
+// Same draws, same first-occurrence order, hence the same result as site_event<..., P16>.
+// *kstat accumulates the number of candidates (for the host's variant choice).
+template <int MODEL, class Fetch>
+__device__ __forceinline__ void site_event_nb26x2(const EventParams &p, int (&cur)[2], const uint32_t (&w)[2][13],
+                                                  const uint4 &blk, Fetch fetch, int *kstat) {
+  constexpr int NN = 26;
+  constexpr bool NULLBIN = MODEL == SPK_POTTS_NEIGH;
+  uint32_t u0[2], rem[2], first[2] = {0u, 0u};
+#pragma unroll
+  for (int h = 0; h < 2; h++) rem[h] = u0[h] = nb26_unequal_mask(w[h], cur[h], p);
+  while (rem[0] | rem[1]) {
+    // per site: the two earliest slots still unexplained; the first one opens a new candidate, the
+    // second one too unless it repeats the first one's value; both are eliminated in one pass.
+    // A site that is done (rem == 0) runs along on bit 31 without effect.
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const uint32_t lo1 = rem[h] & (0u - rem[h]), rest = rem[h] ^ lo1;
+      const uint32_t lo2 = rest ? (rest & (0u - rest)) : lo1;
+      const int c1 = fetch(h, (31 - __clz((int)lo1)) & 31), c2 = fetch(h, (31 - __clz((int)lo2)) & 31);
+      first[h] |= lo1 | (c1 != c2 ? lo2 : 0u);
+      rem[h] &= nb26_unequal_mask2(w[h], c1, c2, p);
+    }
+  }
+  int trial[2], nevent[2];
+  bool live[2];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    nevent[h] = __popc(first[h]);
+    const int pick = (int)__umulhi((uint32_t)(NULLBIN ? NN : nevent[h]), h ? blk.z : blk.x);
+    live[h] = nevent[h] > 0 && (!NULLBIN || pick < nevent[h]);
+    uint32_t f = first[h];
+    for (int i = 0; i < pick && live[h]; i++) f &= f - 1u;  // drop the `pick` earliest candidates
+    trial[h] = fetch(h, (31 - __clz((int)(f & (0u - f)))) & 31);
+  }
+  *kstat += nevent[0] + nevent[1];
+  if (!(live[0] || live[1])) return;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int e0 = __popc(u0[h]);
+    const int e1 = __popc(nb26_unequal_mask(w[h], trial[h], p));
+    const uint32_t w2 = h ? blk.w : blk.y;
+    const bool ok = live[h] && (e1 <= e0 || (!p.t_zero && w2 <= p.thr[e1 > e0 ? e1 - e0 : 0]));
+    cur[h] = ok ? trial[h] : cur[h];
+  }
+}
+
+// the same for one site (sequential variant: the two sites of a chunk one after the other)
+template <int MODEL, class Fetch>
+__device__ __forceinline__ int site_event_nb26(const EventParams &p, int old, const uint32_t (&w)[13],
+                                               uint32_t w1, uint32_t w2, Fetch fetch, int *kstat) {
+  constexpr int NN = 26;
+  constexpr bool NULLBIN = MODEL == SPK_POTTS_NEIGH;
+  const uint32_t u0 = nb26_unequal_mask(w, old, p);
+  if (u0 == 0) return old;  // nevent == 0
+  uint32_t rem = u0, first = 0;
+  do {
+    const uint32_t lo1 = rem & (0u - rem), rest = rem ^ lo1;
+    const uint32_t lo2 = rest ? (rest & (0u - rest)) : lo1;
+    const int c1 = fetch(31 - __clz((int)lo1)), c2 = fetch(31 - __clz((int)lo2));
+    first |= lo1 | (c1 != c2 ? lo2 : 0u);
+    rem &= nb26_unequal_mask2(w, c1, c2, p);
+  } while (rem);
+  const int nevent = __popc(first);
+  *kstat += nevent;
+  const int pick = (int)__umulhi((uint32_t)(NULLBIN ? NN : nevent), w1);
+  if constexpr (NULLBIN) {
+    if (pick >= nevent) return old;
+  }
+  for (int i = 0; i < pick; i++) first &= first - 1u;  // drop the `pick` earliest candidates
+  const int trial = fetch(31 - __clz((int)(first & (0u - first))));
+  const int e0 = __popc(u0);
+  if (e0 == NN) return trial;  // efinal <= einitial whatever the trial
+  const int e1 = __popc(nb26_unequal_mask(w, trial, p));
+  if (e1 <= e0) return trial;
+  if (p.t_zero) return old;
+  return w2 > p.thr[e1 - e0] ? old : trial;
+}
+
 // One site_event_rejection.  `old` = spin[i], v[] = neighbour spins in reference order.
 // Returns the new spin (== old when rejected or no event).
 // P16: every spin of the lattice is <= PK16_MAX_SPIN, compares run on packed pairs (see above).
+// kstat (optional): accumulates nevent of the candidate-list apps (host-side variant choice).
 template <int MODEL, int RNG, int NN, bool P16 = false>
-__device__ __forceinline__ int site_event(const EventParams &p, int old, const int (&v)[NN], Draws<RNG> &d) {
+__device__ __forceinline__ int site_event(const EventParams &p, int old, const int (&v)[NN], Draws<RNG> &d,
+                                          int *kstat = nullptr) {
   const int Q = p.nspins;
   if (MODEL == SPK_POTTS_PIN && old > Q) return old;  // pinned: no draw (src/app_potts_pin.cpp:97)
 
@@ -254,6 +381,7 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
     if constexpr (PK) first = first_occurrence_mask16<NN>(v, negp, old, p);
     else first = first_occurrence_mask<NN>(v, old);
     const int nevent = __popc(first);
+    if (kstat) *kstat += nevent;
     int pick;
     if constexpr (RNG == RNG_PHILOX) {
       pick = (int)__umulhi((uint32_t)(NULLBIN ? NN : nevent), d.w1);

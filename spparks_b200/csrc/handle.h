@@ -43,7 +43,7 @@ struct spk_cuda_handle {
   ncclComm_t comm = nullptr;
   bool tiled = true;  // tuned kernels allowed (SPK_CUDA_FORCE_GENERIC=1 disables, for A/B tests)
   bool use_stream = true;  // SPK_CUDA_NO_STREAM=1 keeps the strip kernel (A/B tests)
-  bool smem_attr_set[9] = {false, false, false, false, false, false, false, false, false};  // dynamic shared memory opt-in done: [0] tile2d, [1..8] stream variants
+  bool smem_attr_set[17] = {};  // dynamic shared memory opt-in done: [0] tile2d, [1..8] stream variants
   uint32_t *cl_label = nullptr, *cl_size = nullptr;  // diag_style cluster: union-find parents, volumes / ids per root
   uint32_t *cl_blocksum = nullptr;
   unsigned long long *cl_count = nullptr;             // [0] ncluster, [1] (as double) sum of radii
@@ -53,6 +53,19 @@ struct spk_cuda_handle {
   bool pk16 = false;       // every spin <= PK16_MAX_SPIN: packed 16-bit compares (SPK_CUDA_NO_PK16=1 disables, for A/B tests)
   bool stream_ok = false;  // TMA streaming kernel usable (3-D lattice, tensor map built)
   CUtensorMap tmap;        // (x, y, plane incl. the two ghost planes) view of the slab
+  CUtensorMap tmap8;       // same view with the box of the 8-class-row tiles (candidate-elimination variant)
+  bool tmap8_ok = false;
+  // candidate-list apps on sc/26n: which first-occurrence algorithm the next launches use
+  // (SPK_CUDA_NEIGH_MODE=chain|adaptive|auto).  auto follows the mean number of distinct neighbour
+  // values per site that the kernels report (kstat), read back without blocking after every sweep.
+  int neigh_mode = 2;            // 0 chain, 1 adaptive, 2 auto
+  bool neigh_adaptive = false;   // current choice
+  unsigned long long *kstat = nullptr;       // device: sum of nevent
+  unsigned long long *kstat_host = nullptr;  // pinned: [0] copy of *kstat, [1] attempts it covers
+  cudaEvent_t ev_kstat = nullptr;
+  bool kstat_pending = false;
+  int64_t kstat_attempt0 = 0;    // h->nattempt when the statistic was last reset
+  double kstat_mean = -1.0;      // last mean read back (-1: none yet)
   int32_t *base_alt = nullptr;  // second lattice buffer of the out-of-place fused 2-D sweep
   CUtensorMap tmap_alt;
   // peer-memory halo (3-D slabs through the streaming kernel): the boundary launches of a colour

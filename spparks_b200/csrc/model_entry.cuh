@@ -107,7 +107,6 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
     return -1;
   } else {
     if (pair && (LAT != SPK_SC_26N || ising_like(MODEL) || (a.c0 & 1) || a.nloop != 1)) return -1;
-    using C = StreamCfg<LAT>;
     const Geo &g = a.g;
     const Box &b = a.b;
     if (!h->stream_ok || b.ilo != 0 || b.ihi != g.X || b.jlo != 0 || b.jhi != g.Y) return -1;
@@ -122,25 +121,28 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
     }
     if (nq <= 0) return 0;
     sm.ntx = (g.X + ST_TX - 1) / ST_TX;
-    sm.nty = (g.Y + C::YT - 1) / C::YT;
     sm.kfirst = kfirst;
     sm.nq = nq;
-    const int grid_max = 2 * 148;
     // work items per resident CTA (plane chunks are cut so that there are about this many): more
     // items balance the tail better, fewer re-read fewer chunk-boundary planes (SPK_CUDA_ITEMS_PER_CTA, A/B tests)
     static const int items_per_cta = [] { const char *e = getenv("SPK_CUDA_ITEMS_PER_CTA"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
-    int nzc = (items_per_cta * grid_max + sm.ntx * sm.nty - 1) / (sm.ntx * sm.nty);
-    if (nzc > nq) nzc = nq;
-    if (nzc < 1) nzc = 1;
-    sm.qchunk = (nq + nzc - 1) / nzc;
-    sm.nzc = (nq + sm.qchunk - 1) / sm.qchunk;
-    sm.items = sm.ntx * sm.nty * sm.nzc;
-    const int grid = sm.items < grid_max ? sm.items : grid_max;
     SweepArgs args = a;  // Geo::lo_wrap / hi_wrap select periodic images (1 GPU) or ghost planes (slabs)
     // P16: packed 16-bit compares (event.cuh) when every spin fits; the Ising shortcut has no compares to pack
-    auto launch = [&](auto ONE, auto PK, auto PAIR) -> int {
+    // AD: candidate elimination for the candidate-list apps (sweep_stream.cuh: ADAPT)
+    auto launch = [&](auto ONE, auto PK, auto PAIR, auto AD) -> int {
       constexpr bool one = decltype(ONE)::value, pk = decltype(PK)::value && !ising_like(MODEL);
       constexpr bool pr = decltype(PAIR)::value && one && LAT == SPK_SC_26N && !ising_like(MODEL);
+      constexpr bool ad = decltype(AD)::value && pk && !pr && LAT == SPK_SC_26N && neigh_like(MODEL);
+      using C = StreamCfgOf<LAT, ad>;
+      const int grid_max = (ad ? ST_ADAPT_MINB : 2) * 148;
+      sm.nty = (g.Y + C::YT - 1) / C::YT;
+      int nzc = (items_per_cta * grid_max + sm.ntx * sm.nty - 1) / (sm.ntx * sm.nty);
+      if (nzc > nq) nzc = nq;
+      if (nzc < 1) nzc = 1;
+      sm.qchunk = (nq + nzc - 1) / nzc;
+      sm.nzc = (nq + sm.qchunk - 1) / sm.qchunk;
+      sm.items = sm.ntx * sm.nty * sm.nzc;
+      const int grid = sm.items < grid_max ? sm.items : grid_max;
       if constexpr (pr) {  // tile-edge words first (stream order: they see the lattice before the pair launch)
         sm.nrows = g.Y / 2;
         const size_t words = 2 * (size_t)sm.ntx * sm.nrows * sm.nq;
@@ -157,21 +159,23 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
         edge_pair_kernel<MODEL, pk><<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(args, sm, h->edge);
         h->launches++;
       }
-      auto *kern = sweep_stream_kernel<LAT, MODEL, one, pk, pr>;
-      bool &attr = h->smem_attr_set[1 + (one ? 0 : 1) + (pk ? 2 : 0) + (pr ? 4 : 0)];
+      auto *kern = sweep_stream_kernel<LAT, MODEL, one, pk, pr, ad>;
+      bool &attr = h->smem_attr_set[1 + (one ? 0 : 1) + (pk ? 2 : 0) + (pr ? 4 : 0) + (ad ? 8 : 0)];
       if (!attr) {  // per handle: the attribute belongs to the device the handle lives on
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) return 1;
         attr = true;
       }
-      kern<<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, args, sm);
+      kern<<<grid, 256, C::SMEM_BYTES, h->stream>>>(ad ? h->tmap8 : h->tmap, args, sm);
       return 0;
     };
     using T = std::true_type;
     using F = std::false_type;
+    const bool adapt = neigh_like(MODEL) && LAT == SPK_SC_26N && h->pk16 && !pair && h->neigh_adaptive && h->tmap8_ok;
     int rc;
-    if (pair) rc = h->pk16 ? launch(T{}, T{}, T{}) : launch(T{}, F{}, T{});
-    else if (args.nloop == 1) rc = h->pk16 ? launch(T{}, T{}, F{}) : launch(T{}, F{}, F{});
-    else rc = h->pk16 ? launch(F{}, T{}, F{}) : launch(F{}, F{}, F{});
+    if (pair) rc = h->pk16 ? launch(T{}, T{}, T{}, F{}) : launch(T{}, F{}, T{}, F{});
+    else if (adapt) rc = args.nloop == 1 ? launch(T{}, T{}, F{}, T{}) : launch(F{}, T{}, F{}, T{});
+    else if (args.nloop == 1) rc = h->pk16 ? launch(T{}, T{}, F{}, F{}) : launch(T{}, F{}, F{}, F{});
+    else rc = h->pk16 ? launch(F{}, T{}, F{}, F{}) : launch(F{}, F{}, F{}, F{});
     if (rc) return rc;
     h->launches++;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
@@ -182,7 +186,7 @@ template <int LAT, int MODEL>
 int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
   SweepArgs a;
   a.spin = h->spin; a.g = h->g; a.c0 = color - 1; a.nloop = nloop; a.ev = h->ev;
-  a.u1 = h->u1; a.u2 = h->u2; a.seeds = h->seeds; a.naccept = h->naccept;
+  a.u1 = h->u1; a.u2 = h->u2; a.seeds = h->seeds; a.naccept = h->naccept; a.kstat = h->kstat;
   a.mirror_lo = h->mirror_active ? h->mirror_lo : nullptr;
   a.mirror_hi = h->mirror_active ? h->mirror_hi : nullptr;
   if (!local_box(h, box, a.b)) return 0;
@@ -207,7 +211,7 @@ int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int
 template <int MODEL> int sweep_pair_m(spk_cuda_handle *h, int color, const int32_t *box) {
   SweepArgs a;
   a.spin = h->spin; a.g = h->g; a.c0 = color - 1; a.nloop = 1; a.ev = h->ev;
-  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept;
+  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept; a.kstat = nullptr;
   a.mirror_lo = h->mirror_active ? h->mirror_lo : nullptr;
   a.mirror_hi = h->mirror_active ? h->mirror_hi : nullptr;
   if (!local_box(h, box, a.b)) return 0;

@@ -186,6 +186,43 @@ int build_tensor_map(spk_cuda_handle *h) {
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   h->stream_ok = (r == CUDA_SUCCESS);
+  h->tmap8_ok = false;
+  if (h->stream_ok && h->d.lattice == SPK_SC_26N && neigh_like(h->d.model) && h->pk16) {
+    cuuint32_t box8[3] = {(cuuint32_t)ST_BX, (cuuint32_t)StreamCfgOf<SPK_SC_26N, true>::RP, 1};
+    r = ((encode_fn)fn)(&h->tmap8, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, h->base, dims, strides, box8, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    h->tmap8_ok = (r == CUDA_SUCCESS);
+  }
+  return 0;
+}
+
+// Candidate-list apps on sc/26n: choose between the all-pairs chain (cost independent of the
+// lattice) and candidate elimination (cost proportional to the distinct neighbour values) from
+// the mean nevent the kernels accumulate in h->kstat.  Called at the first colour of a sweep;
+// never blocks: the statistic is copied to pinned memory behind the launches already queued and
+// picked up one or two sweeps later.  Both variants give identical spins, only the speed differs.
+int neigh_mode_update(spk_cuda_handle *h) {
+  if (!h->kstat || h->neigh_mode != 2) return 0;
+  if (h->kstat_pending && cudaEventQuery(h->ev_kstat) == cudaSuccess) {
+    h->kstat_pending = false;
+    if (h->kstat_host[1] > 0) {
+      h->kstat_mean = (double)h->kstat_host[0] / (double)h->kstat_host[1];
+      // hysteresis around the measured break-even (SPK_CUDA_NEIGH_SWITCH, distinct values per site)
+      static const double sw = [] { const char *e = getenv("SPK_CUDA_NEIGH_SWITCH"); const double v = e ? atof(e) : 0.0; return v > 0.0 ? v : 2.9; }();
+      if (h->kstat_mean < sw - 0.25) h->neigh_adaptive = true;
+      else if (h->kstat_mean > sw + 0.25) h->neigh_adaptive = false;
+    }
+  }
+  cudaGetLastError();  // cudaErrorNotReady of the query is not an error
+  if (!h->kstat_pending && h->nattempt > h->kstat_attempt0) {
+    CU(cudaMemcpyAsync(h->kstat_host, h->kstat, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemsetAsync(h->kstat, 0, sizeof(unsigned long long), h->stream));
+    CU(cudaEventRecord(h->ev_kstat, h->stream));
+    h->kstat_host[1] = (unsigned long long)(h->nattempt - h->kstat_attempt0);
+    h->kstat_attempt0 = h->nattempt;
+    h->kstat_pending = true;
+  }
   return 0;
 }
 
@@ -227,7 +264,7 @@ int fused_sweep(spk_cuda_handle *h, int part) {
   if (!h->tiled || !h->use_fused || h->dim != 2 || !h->fused2d_ok) return -1;
   SweepArgs a;
   a.spin = h->spin; a.g = h->g; a.c0 = 0; a.nloop = 1; a.ev = h->ev;
-  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept;
+  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept; a.kstat = nullptr;
   a.mirror_lo = a.mirror_hi = nullptr;
   a.b = Box{0, h->g.X, 0, h->g.Y, 0, 1};
   if (h->d.nranks == 1 && refresh_ghosts_local(h)) return 1;
@@ -266,6 +303,7 @@ int sweep_set(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nl
   if (color < 1 || color > h->nc) return fail("colour %d out of range 1..%d", color, h->nc);
   if (nloop < 1) return fail("nloop must be >= 1");
   CU(cudaSetDevice(h->d.device));
+  if (color == 1 && rng == RNG_PHILOX && neigh_mode_update(h)) return 1;
   switch (h->d.model) {
     case SPK_ISING: return ModelEntry<SPK_ISING>::sweep_set(h, rng, color, box, nloop);
     case SPK_POTTS: return ModelEntry<SPK_POTTS>::sweep_set(h, rng, color, box, nloop);
@@ -392,6 +430,17 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
     }
   }
   build_tensor_map(h);
+  if (h->tmap8_ok) {
+    const char *nm = getenv("SPK_CUDA_NEIGH_MODE");
+    h->neigh_mode = !nm ? 2 : !strcmp(nm, "chain") ? 0 : !strcmp(nm, "adaptive") ? 1 : 2;
+    h->neigh_adaptive = h->neigh_mode == 1;
+    if (cudaMalloc(&h->kstat, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(h->kstat, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&h->kstat_host, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_kstat, cudaEventDisableTiming) != cudaSuccess)
+      return cleanup(fail("allocation of the candidate statistic failed"));
+    h->kstat_host[0] = h->kstat_host[1] = 0;
+  }
   if (cudaMalloc(&h->naccept, 2 * sizeof(unsigned long long)) != cudaSuccess) return cleanup(fail("cudaMalloc failed"));
   h->escratch = h->naccept + 1;
   cudaMemset(h->naccept, 0, 2 * sizeof(unsigned long long));
@@ -418,6 +467,9 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   }
   cudaFree(h->flags);
   cudaFree(h->edge);
+  cudaFree(h->kstat);
+  if (h->kstat_host) cudaFreeHost(h->kstat_host);
+  if (h->ev_kstat) cudaEventDestroy(h->ev_kstat);
   cudaFree(h->cl_label); cudaFree(h->cl_size); cudaFree(h->cl_blocksum); cudaFree(h->cl_count);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->base); cudaFree(h->base_alt); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
@@ -776,6 +828,13 @@ int spk_cuda_reset_counters(spk_cuda_handle *h) {
   CU(cudaSetDevice(h->d.device));
   CU(cudaMemsetAsync(h->naccept, 0, sizeof(unsigned long long), h->stream));
   h->nattempt = 0;
+  return 0;
+}
+
+int spk_cuda_neigh_variant(spk_cuda_handle *h, int *variant, double *mean_distinct) {
+  if (!h || !variant) return fail("null argument");
+  *variant = h->tmap8_ok && h->tiled && h->use_stream ? (h->neigh_adaptive ? 1 : 0) : -1;
+  if (mean_distinct) *mean_distinct = h->kstat_mean;
   return 0;
 }
 

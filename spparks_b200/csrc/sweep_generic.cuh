@@ -17,6 +17,7 @@ struct SweepArgs {
   const double *u1, *u2;  // RNG_INJECTED: per owned site
   int32_t *seeds;         // RNG_STRICT: per owned site
   unsigned long long *naccept;
+  unsigned long long *kstat;  // candidate-list apps: sum of nevent over the sites (streaming kernel; null = off)
   // peer-memory halo (streaming kernel, multi-GPU slabs): updates of local plane 0 / Z-1 are also
   // stored into the ring neighbour's ghost plane over NVLink (null = no mirror)
   int32_t *mirror_lo, *mirror_hi;

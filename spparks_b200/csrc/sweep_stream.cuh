@@ -23,15 +23,20 @@ constexpr int ST_TX = 128;        // tile width in sites: 32 lanes x one 16-byte
 constexpr int ST_BX = ST_TX + 8;  // TMA box inner extent
 constexpr int ST_CR = 16;         // class rows per tile: 8 warps x 2
 
-template <int LAT> struct StreamCfg {
+// CRows = class rows per tile (a multiple of the 8 warps): 16 for the register-heavy variants
+// (2 CTAs per SM), 8 for the candidate-elimination variant (half the shared memory, 4 CTAs per SM)
+template <int LAT, int CRows = ST_CR> struct StreamCfg {
+  static constexpr int CR = CRows;
   static constexpr int JSTEP = (LAT == SPK_SC_26N) ? 2 : 1;  // class rows / planes are every
   static constexpr int KSTEP = (LAT == SPK_SC_26N) ? 2 : 1;  // JSTEP-th row / KSTEP-th plane
-  static constexpr int YT = ST_CR * JSTEP;                   // lattice rows per tile
+  static constexpr int YT = CR * JSTEP;                      // lattice rows per tile
   static constexpr int RP = YT + 2;                          // rows per plane in smem (y halo)
   static constexpr int RING = 3 + KSTEP;                     // stencil window + planes in flight
   static constexpr int PLANE_BYTES = ST_BX * RP * 4;
   static constexpr int PLANE_STRIDE = (PLANE_BYTES + 127) / 128 * 128;
-  static constexpr int SMEM_BYTES = RING * PLANE_STRIDE + 8 * RING;
+  static constexpr int BAR_OFF = RING * PLANE_STRIDE;        // mbarriers, one per ring slot
+  static constexpr int TAB_OFF = BAR_OFF + 64;               // nb26 offset tables (candidate elimination)
+  static constexpr int SMEM_BYTES = TAB_OFF + RING * 32 * 4;
 };
 
 struct StreamMap {
@@ -76,9 +81,8 @@ struct PatchPlan {
   int gx_l, gx_r;    // lattice x of the periodic images of those columns
 };
 
-template <int LAT>
+template <class C>
 __device__ __forceinline__ PatchPlan make_patch_plan(int x0, int y0, int rowlen, int Y) {
-  using C = StreamCfg<LAT>;
   PatchPlan pp;
   pp.col_l = x0 == 0 ? 3 : -1;
   pp.gx_l = rowlen - 1;
@@ -91,10 +95,9 @@ __device__ __forceinline__ PatchPlan make_patch_plan(int x0, int y0, int rowlen,
   return pp;
 }
 
-template <int LAT>
+template <class C>
 __device__ __forceinline__ void patch_load(const PatchPlan &pp, const int32_t *gplane, int x0, int y0, int rowlen,
                                            int Y, int tid, int (&v)[2]) {
-  using C = StreamCfg<LAT>;
   v[0] = v[1] = 0;
   if (tid < C::RP) {  // my row of the two columns
     int y = y0 - 1 + tid;
@@ -114,9 +117,8 @@ __device__ __forceinline__ void patch_load(const PatchPlan &pp, const int32_t *g
   }
 }
 
-template <int LAT>
+template <class C>
 __device__ __forceinline__ void patch_store(const PatchPlan &pp, int32_t *pl, int tid, const int (&v)[2]) {
-  using C = StreamCfg<LAT>;
   if (tid < C::RP) {
     if (pp.col_l >= 0) pl[tid * ST_BX + pp.col_l] = v[0];
     if (pp.col_r >= 0) pl[tid * ST_BX + pp.col_r] = v[1];
@@ -129,7 +131,8 @@ __device__ __forceinline__ void patch_store(const PatchPlan &pp, int32_t *pl, in
 // one class row of one class plane: the thread's 16-byte chunk holds two class sites at P, P+2
 template <int LAT, int MODEL, int P, bool ONEPASS, bool P16>
 __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *const (&pl)[3], int r, int lane,
-                                            int32_t *gchunk, int32_t *gmirror, unsigned long long gsite0, int xcell) {
+                                            int32_t *gchunk, int32_t *gmirror, unsigned long long gsite0, int xcell,
+                                            int *kstat = nullptr) {
   using L = Lat<LAT>;
   constexpr int NN = L::NN;
   using R = RowInfo<LAT, 0>;
@@ -174,7 +177,7 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
         d.w1 = h ? blk.z : blk.x;
         d.w2 = h ? blk.w : blk.y;
       }
-      const int nw = site_event<MODEL, RNG_PHILOX, NN, P16>(a.ev, cur[h], v, d);
+      const int nw = site_event<MODEL, RNG_PHILOX, NN, P16>(a.ev, cur[h], v, d, kstat);
       accepted += (nw != cur[h]);
       cur[h] = nw;
     });
@@ -183,6 +186,78 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
     W[4][1 + P] = cur[0];
     W[4][3 + P] = cur[1];
     const int4 nv = make_int4(W[4][1], W[4][2], W[4][3], W[4][4]);
+    *reinterpret_cast<int4 *>(gchunk) = nv;
+    if (gmirror) *reinterpret_cast<int4 *>(gmirror) = nv;  // the neighbour's ghost copy of this chunk
+  }
+  return accepted;
+}
+
+// The same chunk for the candidate-list apps on sc/26n by candidate elimination (event.cuh:
+// site_event_nb26).  The packed neighbour words of both sites are built first so that the
+// register window is dead before the per-site loops start; a candidate's value is read back from
+// the shared-memory planes: nbtab[b] = byte offset of the neighbour behind mask bit b relative to
+// the site itself.
+template <int MODEL, int P, bool ONEPASS>
+__device__ __forceinline__ int stream_chunk_nb26(const SweepArgs &a, const int32_t *const (&pl)[3], int r, int lane,
+                                                 int32_t *gchunk, int32_t *gmirror, unsigned long long gsite0,
+                                                 const int *nbtab, int *kstat) {
+  using L = Lat<SPK_SC_26N>;
+  const int32_t *own = pl[1] + r * ST_BX + 4 + 4 * lane;
+  uint32_t wd[2][13];
+  {
+    int W[9][5];  // W[row][e - P + 1]: elements P-1 .. P+3 of the chunk's stencil rows
+    static_for<9>([&](auto RR) {
+      constexpr int rr = decltype(RR)::value, dy = rr % 3 - 1, dz = rr / 3 - 1;
+      const int32_t *rowp = pl[dz + 1] + (r + dy) * ST_BX + 4 + 4 * lane;
+      const int4 t = *reinterpret_cast<const int4 *>(rowp);
+      if constexpr (P == 0) { W[rr][0] = rowp[-1]; W[rr][1] = t.x; W[rr][2] = t.y; W[rr][3] = t.z; W[rr][4] = t.w; }
+      else { W[rr][0] = t.x; W[rr][1] = t.y; W[rr][2] = t.z; W[rr][3] = t.w; W[rr][4] = rowp[4]; }
+    });
+    static_for<2>([&](auto H) {
+      constexpr int h = decltype(H)::value;
+      static_for<13>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        constexpr Off o0 = L::off(0, j), o1 = L::off(0, j + 13);
+        wd[h][j] = pk_negpair(W[(o0.dz + 1) * 3 + (o0.dy + 1)][1 + 2 * h + o0.dx],
+                              W[(o1.dz + 1) * 3 + (o1.dy + 1)][1 + 2 * h + o1.dx], a.ev);
+      });
+    });
+  }
+  const int4 chunk = *reinterpret_cast<const int4 *>(own);
+  int cur[2] = {P ? chunk.y : chunk.x, P ? chunk.w : chunk.z};
+  const int before0 = cur[0], before1 = cur[1];
+  int accepted = 0;
+  const unsigned long long leader = gsite0 + P;
+  const uint32_t tab = smem_u32(nbtab);
+  const int nloop = ONEPASS ? 1 : a.nloop;
+#pragma unroll
+  for (int l = 0; l < nloop; l++) {
+    const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep,
+                                    (uint32_t)l * 16u + (uint32_t)(a.c0 + 1), a.ev.rk);
+    const uint32_t self = smem_u32(own + P);
+    const int prev0 = cur[0], prev1 = cur[1];
+#if ST_NB26_JOINT
+    site_event_nb26x2<MODEL>(a.ev, cur, wd, blk, [&](int h, int b) {
+      int off, val;
+      asm("ld.shared.s32 %0, [%1];" : "=r"(off) : "r"(tab + 4u * (uint32_t)b));
+      asm("ld.shared.s32 %0, [%1];" : "=r"(val) : "r"(self + 8u * (uint32_t)h + (uint32_t)off));
+      return val;
+    }, kstat);
+#else
+    static_for<2>([&](auto H) {
+      constexpr int h = decltype(H)::value;
+      cur[h] = site_event_nb26<MODEL>(a.ev, cur[h], wd[h], h ? blk.z : blk.x, h ? blk.w : blk.y, [&](int b) {
+        int off, val;
+        asm("ld.shared.s32 %0, [%1];" : "=r"(off) : "r"(tab + 4u * (uint32_t)b));
+        asm("ld.shared.s32 %0, [%1];" : "=r"(val) : "r"(self + 8u * h + (uint32_t)off));
+        return val;
+      }, kstat);
+    });
+#endif
+    accepted += (cur[0] != prev0) + (cur[1] != prev1);
+  }
+  if (cur[0] != before0 || cur[1] != before1) {
+    const int4 nv = P ? make_int4(chunk.x, cur[0], chunk.z, cur[1]) : make_int4(cur[0], chunk.y, cur[1], chunk.w);
     *reinterpret_cast<int4 *>(gchunk) = nv;
     if (gmirror) *reinterpret_cast<int4 *>(gmirror) = nv;  // the neighbour's ghost copy of this chunk
   }
@@ -291,17 +366,26 @@ __global__ void __launch_bounds__(256) edge_pair_kernel(const __grid_constant__ 
   edge[2 * idx + 1] = site_event<MODEL, RNG_PHILOX, NN, P16>(a.ev, cur, v, d);
 }
 
-template <int LAT, int MODEL, bool ONEPASS, bool P16, bool PAIR = false>
-#ifndef ST_MINB
-#define ST_MINB 2
+// ADAPT (sc/26n candidate-list apps, packed spins): candidate elimination, 8 class rows per tile
+// and 4 CTAs per SM (the per-site loop is latency bound: more resident warps, fewer registers)
+#ifndef ST_NB26_JOINT
+#define ST_NB26_JOINT 0  // 1: both sites of a chunk in one loop (measured slower: the loop runs to the warp maximum over 64 sites)
 #endif
-__global__ void __launch_bounds__(256, (MODEL == SPK_POTTS_NEIGHONLY && P16) ? ST_MINB : 2)
+#ifndef ST_ADAPT_MINB
+#define ST_ADAPT_MINB 3
+#endif
+template <int LAT, bool ADAPT> using StreamCfgOf = StreamCfg<LAT, ADAPT ? 8 : ST_CR>;
+
+template <int LAT, int MODEL, bool ONEPASS, bool P16, bool PAIR = false, bool ADAPT = false>
+__global__ void __launch_bounds__(256, ADAPT ? ST_ADAPT_MINB : 2)
 sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SweepArgs a,
                     const __grid_constant__ StreamMap sm) {
-  using C = StreamCfg<LAT>;
+  using C = StreamCfgOf<LAT, ADAPT>;
+  constexpr int TPW = C::CR / 8;  // class rows per warp
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + C::RING * C::PLANE_STRIDE);
-  auto plane_ptr = [&](uint32_t seq) { return reinterpret_cast<int32_t *>(smem_raw + (seq % C::RING) * C::PLANE_STRIDE); };
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + C::BAR_OFF);
+  int *nbtabs = reinterpret_cast<int *>(smem_raw + C::TAB_OFF);
+  auto plane_ptr = [&](uint32_t slot) { return reinterpret_cast<int32_t *>(smem_raw + slot * C::PLANE_STRIDE); };
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Geo &g = a.g;
@@ -312,20 +396,44 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     for (int i = 0; i < C::RING; i++) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if constexpr (ADAPT) {
+    // nbtabs[c][b]: the window's middle plane sits in ring slot (c + 1) % RING; bit b -> slot ->
+    // (dx,dy,dz) in reference order (lattice.cuh) -> byte offset from the site's own element
+    if (tid < C::RING * 32) {
+      const int c = tid >> 5, b = tid & 31;
+      int off = 0;
+      if ((NB26_VALID >> b) & 1) {
+        const Off o = Lat<SPK_SC_26N>::off(0, nb26_bit_to_slot(b));
+        const int mid = (c + 1) % C::RING, pln = (c + 1 + o.dz + C::RING) % C::RING;
+        off = (pln - mid) * C::PLANE_STRIDE + (o.dy * ST_BX + o.dx) * 4;
+      }
+      nbtabs[tid] = off;
+    }
+  }
   __syncthreads();
 
   // plane kk in -1..Z -> plane that holds it: the periodic image on one GPU (lo_wrap = Z-1,
   // hi_wrap = 0), the ghost plane of the slab otherwise (lo_wrap = -1, hi_wrap = Z)
   auto zmap = [&](int kk) { return kk < 0 ? g.lo_wrap : (kk >= g.Z ? g.hi_wrap : kk); };
-  auto issue = [&](int kk, uint32_t seq, int x0, int y0) {  // plane kk (local, -1..Z) as sequence number seq
-    uint64_t *bar = &full[seq % C::RING];
+  // Ring bookkeeping without divisions: `slot` = ring slot of the window's first plane (k-1),
+  // advanced with a compare-and-subtract; `phase` bit i = parity the next wait on barrier i expects
+  // (every use of a slot is one TMA box and one wait by every thread).  All CTA-uniform.
+  auto adv = [](uint32_t sl, uint32_t d) { sl += d; return sl >= (uint32_t)C::RING ? sl - C::RING : sl; };
+  uint32_t slot = 0, phase = 0;
+  auto issue = [&](int kk, uint32_t sl, int x0, int y0) {  // plane kk (local, -1..Z) into ring slot sl
+    uint64_t *bar = &full[sl];
     mbar_expect_tx(bar, C::PLANE_BYTES);
-    tma_load_3d(plane_ptr(seq), &tmap, bar, x0 - 4, y0 - 1, zmap(kk) + 1);  // tensor plane 0 = lower ghost plane
+    tma_load_3d(plane_ptr(sl), &tmap, bar, x0 - 4, y0 - 1, zmap(kk) + 1);  // tensor plane 0 = lower ghost plane
   };
-  auto wait = [&](uint32_t seq) { mbar_wait(&full[seq % C::RING], (seq / C::RING) & 1u); };
+  auto wait = [&](uint32_t sl) {
+    mbar_wait(&full[sl], (phase >> sl) & 1u);
+    phase ^= 1u << sl;
+  };
 
-  uint32_t Q = 0;  // running plane sequence number: slot = Q % RING, barrier parity = (Q / RING) & 1
   int accepted = 0;
+  [[maybe_unused]] int kstat = 0;  // candidate-list apps: sum of nevent over this thread's sites
+  const bool mirrors = a.mirror_lo != nullptr || a.mirror_hi != nullptr;  // boundary launches of a slab run only
+  const unsigned long long plane_sites = (unsigned long long)g.gY * (unsigned long long)g.gX;
   for (int item = blockIdx.x; item < sm.items; item += gridDim.x) {
     const int tx = item % sm.ntx, ty = (item / sm.ntx) % sm.nty, zc = item / (sm.ntx * sm.nty);
     const int x0 = tx * ST_TX, y0 = ty * C::YT;
@@ -333,79 +441,81 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     const int kstart = sm.kfirst + q0 * C::KSTEP;
     const bool edge = x0 == 0 || x0 + ST_TX >= rowlen || y0 == 0 || y0 + C::YT >= Y;
 
-    const PatchPlan pp = make_patch_plan<LAT>(x0, y0, rowlen, Y);
+    const PatchPlan pp = make_patch_plan<C>(x0, y0, rowlen, Y);
 
     if (tid == 0)
-      for (int p = 0; p < 3; p++) issue(kstart - 1 + p, Q + p, x0, y0);
+      for (int p = 0; p < 3; p++) issue(kstart - 1 + p, adv(slot, p), x0, y0);
     if (edge) {  // prologue: the three planes of the first stencil window
       int pv0[3][2];
       for (int p = 0; p < 3; p++)
-        patch_load<LAT>(pp, a.spin + (long long)zmap(kstart - 1 + p) * sz, x0, y0, rowlen, Y, tid, pv0[p]);
+        patch_load<C>(pp, a.spin + (long long)zmap(kstart - 1 + p) * sz, x0, y0, rowlen, Y, tid, pv0[p]);
       for (int p = 0; p < 3; p++) {
-        wait(Q + p);
-        patch_store<LAT>(pp, plane_ptr(Q + p), tid, pv0[p]);
+        wait(adv(slot, p));
+        patch_store<C>(pp, plane_ptr(adv(slot, p)), tid, pv0[p]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
     }
 
-    // the two class rows of this warp: everything that does not depend on the plane is computed
-    // once per item; the plane-dependent parts are running values advanced per step
+    // the class rows of this warp: everything that does not depend on the plane is computed once
+    // per item; the plane-dependent parts are running pointers / indices advanced per step
     const int x = x0 + 4 * lane;
-    int yrow[2];
-    long long rowoff[2];            // element offset of the thread's chunk inside a plane
-    unsigned long long rowsite[2];  // its global site index inside a plane
+    int yrow[TPW];
+    bool live[TPW];
+    int32_t *gptr[TPW];            // the thread's chunk in plane k of the lattice
+    unsigned long long gsite[TPW];  // its global site index
 #pragma unroll
-    for (int t = 0; t < 2; t++) {
+    for (int t = 0; t < TPW; t++) {
       const int cr = warp + 8 * t;
       yrow[t] = LAT == SPK_SC_26N ? y0 + 2 * cr + ((a.c0 >> 1) & 1) : y0 + cr;
-      rowoff[t] = (long long)yrow[t] * sy + x;
-      rowsite[t] = (unsigned long long)yrow[t] * (unsigned long long)g.gX + x;
+      live[t] = yrow[t] < Y && (PAIR || x < rowlen);  // y: warp-uniform; PAIR: lanes past the row end run along (shuffle)
+      gptr[t] = a.spin + ((long long)kstart * sz + (long long)yrow[t] * sy + x);
+      gsite[t] = ((unsigned long long)(kstart + g.g0) * g.gY + yrow[t]) * (unsigned long long)g.gX + x;
     }
-    int32_t *kbase = a.spin + (long long)kstart * sz;  // plane k of the lattice
-    unsigned long long ksite = (unsigned long long)(kstart + g.g0) * g.gY * (unsigned long long)g.gX;
-    const bool mirrors = a.mirror_lo != nullptr || a.mirror_hi != nullptr;  // boundary launches of a slab run only
 
     int pv[C::KSTEP][2];  // patch values of the planes in flight
-    for (int s = 0; s < nsteps; s++, kbase += C::KSTEP * sz, ksite += (unsigned long long)C::KSTEP * g.gY * g.gX) {
+    for (int s = 0; s < nsteps; s++) {
       const int k = kstart + s * C::KSTEP;
-      const uint32_t Qs = Q + s * C::KSTEP;  // sequence number of plane k-1
+      const uint32_t w0 = slot, w1 = adv(slot, 1), w2 = adv(slot, 2);  // planes k-1, k, k+1
 
       if (s > 0) {  // planes k .. k+KSTEP-1 shifted into the window: wait, then patch
-        for (int p = 0; p < C::KSTEP; p++) wait(Qs + 3 - C::KSTEP + p);
+        for (int p = 0; p < C::KSTEP; p++) wait(adv(slot, 3 - C::KSTEP + p));
         if (edge) {
-          for (int p = 0; p < C::KSTEP; p++) patch_store<LAT>(pp, plane_ptr(Qs + 3 - C::KSTEP + p), tid, pv[p]);
+          for (int p = 0; p < C::KSTEP; p++) patch_store<C>(pp, plane_ptr(adv(slot, 3 - C::KSTEP + p)), tid, pv[p]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncthreads();
         }
       } else if (!edge) {
-        for (int p = 0; p < 3; p++) wait(Qs + p);
+        wait(w0); wait(w1); wait(w2);
       }
 
       if (s + 1 < nsteps) {  // next step's planes: TMA boxes and (edge tiles) their patch loads
         if (tid == 0)
-          for (int p = 0; p < C::KSTEP; p++) issue(k + 2 + p, Qs + 3 + p, x0, y0);
+          for (int p = 0; p < C::KSTEP; p++) issue(k + 2 + p, adv(slot, 3 + p), x0, y0);
         if (edge)
           for (int p = 0; p < C::KSTEP; p++)
-            patch_load<LAT>(pp, a.spin + (long long)zmap(k + 2 + p) * sz, x0, y0, rowlen, Y, tid, pv[p]);
+            patch_load<C>(pp, a.spin + (long long)zmap(k + 2 + p) * sz, x0, y0, rowlen, Y, tid, pv[p]);
       }
 
-      const int32_t *const pl[3] = {plane_ptr(Qs), plane_ptr(Qs + 1), plane_ptr(Qs + 2)};
-      int32_t *mbase = nullptr;  // ghost plane of the ring neighbour that mirrors plane k (CTA-uniform)
+      const int32_t *const pl[3] = {plane_ptr(w0), plane_ptr(w1), plane_ptr(w2)};
+      long long moff = 0;  // byte distance plane k -> the ring neighbour's ghost plane that mirrors it (CTA-uniform)
+      bool mirror = false;
       if (mirrors) {
-        if (k == 0 && a.mirror_lo) mbase = a.mirror_lo;
-        if (k == g.Z - 1 && a.mirror_hi) mbase = a.mirror_hi;
+        const long long here = reinterpret_cast<long long>(a.spin + (long long)k * sz);
+        if (k == 0 && a.mirror_lo) { mirror = true; moff = reinterpret_cast<long long>(a.mirror_lo) - here; }
+        if (k == g.Z - 1 && a.mirror_hi) { mirror = true; moff = reinterpret_cast<long long>(a.mirror_hi) - here; }
       }
+      [[maybe_unused]] const int *nbtab = nbtabs + w0 * 32;
 #pragma unroll
-      for (int t = 0; t < 2; t++) {
+      for (int t = 0; t < TPW; t++) {
         const int y = yrow[t];
         const int px = LAT == SPK_SC_26N ? (a.c0 & 1) : ((a.c0 + y + k + g.g0) & 1);
-        int32_t *gchunk = kbase + rowoff[t];
-        int32_t *gmirror = mbase ? mbase + rowoff[t] : nullptr;
-        const unsigned long long gsite0 = ksite + rowsite[t];
-        if constexpr (PAIR) {
-          if (y < Y) {  // warp-uniform; lanes past the row end run along (shuffle) without storing
-            const int r = y - y0 + 1;
+        int32_t *gchunk = gptr[t];
+        int32_t *gmirror = mirror ? reinterpret_cast<int32_t *>(reinterpret_cast<long long>(gchunk) + moff) : nullptr;
+        const unsigned long long gsite0 = gsite[t];
+        if (live[t]) {
+          const int r = y - y0 + 1;
+          if constexpr (PAIR) {
             const bool valid = x < rowlen;
             const long long ebase = ((long long)(q0 + s) * sm.nrows + (y >> 1)) * sm.ntx;
             const bool use_left = lane == 0, use_right = valid && (lane == 31 || x + 4 >= rowlen);
@@ -414,19 +524,31 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             if (use_right) right_new = sm.edge[2 * (ebase + (x + 4 >= rowlen ? 0 : tx + 1)) + 1];
             accepted += stream_chunk_pair<LAT, MODEL, P16>(a, pl, r, lane, valid, gchunk, gmirror, gsite0, use_left,
                                                            left_pre, use_right, right_new);
+          } else if constexpr (ADAPT) {
+            static_assert(!ADAPT || (LAT == SPK_SC_26N && P16 && neigh_like(MODEL)), "candidate elimination: sc/26n candidate-list apps, packed spins");
+            if (px) accepted += stream_chunk_nb26<MODEL, 1, ONEPASS>(a, pl, r, lane, gchunk, gmirror, gsite0, nbtab, &kstat);
+            else accepted += stream_chunk_nb26<MODEL, 0, ONEPASS>(a, pl, r, lane, gchunk, gmirror, gsite0, nbtab, &kstat);
+          } else {
+            if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x, &kstat);
+            else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x, &kstat);
           }
-        } else if (y < Y && x < rowlen) {  // y: warp-uniform
-          const int r = y - y0 + 1;
-          if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x);
-          else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x);
         }
+        gptr[t] += C::KSTEP * sz;
+        gsite[t] += (unsigned long long)C::KSTEP * plane_sites;
       }
       __syncthreads();  // planes k-1 (and k) may now be overwritten by the next step's loads
+      if (s + 1 < nsteps) slot = adv(slot, C::KSTEP);
     }
-    Q += 3 + (nsteps - 1) * C::KSTEP;
+    slot = adv(slot, 3);  // the last window's three slots are free again (everybody passed the barrier)
   }
   accepted = __reduce_add_sync(0xffffffffu, accepted);
   if (lane == 0 && accepted) atomicAdd(a.naccept, (unsigned long long)accepted);
+  if constexpr (neigh_like(MODEL)) {
+    if (a.kstat) {
+      kstat = __reduce_add_sync(0xffffffffu, kstat);
+      if (lane == 0 && kstat) atomicAdd(a.kstat, (unsigned long long)kstat);
+    }
+  }
 }
 
 }  // namespace spk

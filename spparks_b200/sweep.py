@@ -150,6 +150,13 @@ class LatticeSweep:
         """0 = single GPU, 1 = NCCL exchange per colour step, 2 = peer-memory stores (no exchange)."""
         return int(self.L.spk_cuda_halo_mode(self.h))
 
+    def neigh_variant(self, with_mean=False):
+        """Candidate-list apps on sc/26n: "chain" | "adaptive" (None when not applicable)."""
+        v, m = C.c_int(), C.c_double()
+        _lib.check(self.L.spk_cuda_neigh_variant(self.h, C.byref(v), C.byref(m)))
+        name = {0: "chain", 1: "adaptive"}.get(v.value)
+        return (name, m.value) if with_mean else name
+
     # -- stream / timing -----------------------------------------------------------------------
     def sync(self):
         _lib.check(self.L.spk_cuda_sync(self.h))

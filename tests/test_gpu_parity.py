@@ -131,12 +131,26 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("model,lat,n,q,T", CASES, ids=lambda v: str(v).replace(" ", ""))
-@pytest.mark.parametrize("kernel", ["tuned", "tuned32", "pair", "strip", "generic"])
+def _kernel_cases():
+    out = []
+    for c in CASES:
+        for kernel in ["tuned", "tuned32", "pair", "strip", "generic"]:
+            out.append(c + (kernel,))
+        if c[0] in ("potts/neighonly", "potts/neigh") and c[1] == "sc/26n":
+            out.append(c + ("adaptive",))  # candidate elimination instead of the all-pairs chain
+    return out
+
+
+@pytest.mark.parametrize("model,lat,n,q,T,kernel", _kernel_cases(), ids=lambda v: str(v).replace(" ", ""))
 def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, kernel, monkeypatch):
     """Production (Philox) mode, three full sweeps, through every kernel family (TMA streaming
     kernel where it applies — colour-pair launches, per-colour launches, packed 16-bit and 32-bit
-    compares —, strip kernel, generic kernel): bit-exact against the oracle evaluating the same counter-based stream."""
+    compares, candidate elimination —, strip kernel, generic kernel): bit-exact against the oracle
+    evaluating the same counter-based stream."""
+    if kernel == "adaptive":
+        monkeypatch.setenv("SPK_CUDA_NEIGH_MODE", "adaptive")
+    if kernel == "tuned":
+        monkeypatch.setenv("SPK_CUDA_NEIGH_MODE", "chain")
     if kernel == "generic":
         monkeypatch.setenv("SPK_CUDA_FORCE_GENERIC", "1")
     if kernel == "tuned32":
@@ -181,6 +195,39 @@ def test_packed16_extreme_spin_values(model, q):
     s.sweeps(0, 3)
     assert np.array_equal(s.download(), want)
     assert s.counters() == (nacc, 3 * o.nsites)
+
+
+@pytest.mark.parametrize("model", ["potts/neighonly", "potts/neigh"])
+@pytest.mark.parametrize("mode", ["adaptive", "auto"])
+@pytest.mark.parametrize("start", ["random", "grains", "two-values"])
+def test_candidate_elimination_vs_oracle(model, mode, start, monkeypatch):
+    """sc/26n candidate-list apps: the candidate-elimination kernel (work ~ distinct neighbour values)
+    and the automatic switch between it and the all-pairs chain, over a run that coarsens from 26
+    distinct neighbours to a few; also from lattices that start with few distinct values (grains,
+    a two-valued lattice where most sites have no event).  Several x/y tiles and plane chunks."""
+    monkeypatch.setenv("SPK_CUDA_NEIGH_MODE", mode)
+    monkeypatch.setenv("SPK_CUDA_NEIGH_SWITCH", "9")  # auto: switch early enough to happen inside the run
+    rng = np.random.default_rng(77)
+    n, q, T, seed = (136, 38, 12), 5000, 0.4, 0xABCDEF
+    o = O.Oracle(model, "sc/26n", n[0], n[1], n[2], q, T)
+    if start == "random":
+        spins = rng.integers(1, q + 1, size=o.nsites, dtype=np.int32)
+    elif start == "grains":  # 4 x 4 x 3 blocks of one value
+        g = rng.integers(1, q + 1, size=(n[2] // 3, (n[1] + 3) // 4, n[0] // 4), dtype=np.int32)
+        spins = np.repeat(np.repeat(np.repeat(g, 3, 0), 4, 1), 4, 2)[:, :n[1], :].reshape(-1).copy()
+    else:
+        spins = np.where(rng.random(o.nsites) < 0.03, 7, 4999).astype(np.int32)
+    s = _sweep(model, "sc/26n", n, q, T, seed=seed)
+    s.upload(spins)
+    want = spins.copy()
+    nsweeps = 10
+    nacc = sum(o.sweep_philox(want, seed, sw) for sw in range(nsweeps))
+    for sw in range(nsweeps):  # one call per sweep: the automatic mode re-decides at each first colour
+        s.sweeps(sw, 1)
+    assert np.array_equal(s.download(), want)
+    assert s.counters() == (nacc, nsweeps * o.nsites)
+    if mode == "auto":
+        assert s.neigh_variant() in ("chain", "adaptive")
 
 
 def test_per_colour_calls_equal_fused_sweeps():
