@@ -132,9 +132,9 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
     auto launch = [&](auto ONE, auto PK, auto PAIR, auto AD) -> int {
       constexpr bool one = decltype(ONE)::value, pk = decltype(PK)::value && !ising_like(MODEL);
       constexpr bool pr = decltype(PAIR)::value && one && LAT == SPK_SC_26N && !ising_like(MODEL);
-      constexpr bool ad = decltype(AD)::value && pk && !pr && LAT == SPK_SC_26N && neigh_like(MODEL);
+      constexpr int ad = (pk && !pr && LAT == SPK_SC_26N && neigh_like(MODEL)) ? decltype(AD)::value : 0;
       using C = StreamCfgOf<LAT, ad>;
-      const int grid_max = (ad ? ST_ADAPT_MINB : 2) * 148;
+      const int grid_max = stream_min_blocks(ad) * 148;
       sm.nty = (g.Y + C::YT - 1) / C::YT;
       int nzc = (items_per_cta * grid_max + sm.ntx * sm.nty - 1) / (sm.ntx * sm.nty);
       if (nzc > nq) nzc = nq;
@@ -160,7 +160,7 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
         h->launches++;
       }
       auto *kern = sweep_stream_kernel<LAT, MODEL, one, pk, pr, ad>;
-      bool &attr = h->smem_attr_set[1 + (one ? 0 : 1) + (pk ? 2 : 0) + (pr ? 4 : 0) + (ad ? 8 : 0)];
+      bool &attr = h->smem_attr_set[1 + (one ? 0 : 1) + (pk ? 2 : 0) + (pr ? 4 : 0) + 8 * ad];
       if (!attr) {  // per handle: the attribute belongs to the device the handle lives on
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) return 1;
         attr = true;
@@ -170,12 +170,15 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
     };
     using T = std::true_type;
     using F = std::false_type;
-    const bool adapt = neigh_like(MODEL) && LAT == SPK_SC_26N && h->pk16 && !pair && h->neigh_adaptive && h->tmap8_ok;
+    using V0 = std::integral_constant<int, 0>;
+    using V1 = std::integral_constant<int, 1>;
+    const bool nb8 = neigh_like(MODEL) && LAT == SPK_SC_26N && h->pk16 && !pair && h->tmap8_ok;
+    const bool adapt = nb8 && h->neigh_adaptive;
     int rc;
-    if (pair) rc = h->pk16 ? launch(T{}, T{}, T{}, F{}) : launch(T{}, F{}, T{}, F{});
-    else if (adapt) rc = args.nloop == 1 ? launch(T{}, T{}, F{}, T{}) : launch(F{}, T{}, F{}, T{});
-    else if (args.nloop == 1) rc = h->pk16 ? launch(T{}, T{}, F{}, F{}) : launch(T{}, F{}, F{}, F{});
-    else rc = h->pk16 ? launch(F{}, T{}, F{}, F{}) : launch(F{}, F{}, F{}, F{});
+    if (pair) rc = h->pk16 ? launch(T{}, T{}, T{}, V0{}) : launch(T{}, F{}, T{}, V0{});
+    else if (adapt) rc = args.nloop == 1 ? launch(T{}, T{}, F{}, V1{}) : launch(F{}, T{}, F{}, V1{});
+    else if (args.nloop == 1) rc = h->pk16 ? launch(T{}, T{}, F{}, V0{}) : launch(T{}, F{}, F{}, V0{});
+    else rc = h->pk16 ? launch(F{}, T{}, F{}, V0{}) : launch(F{}, F{}, F{}, V0{});
     if (rc) return rc;
     h->launches++;
     return cudaGetLastError() == cudaSuccess ? 0 : 1;

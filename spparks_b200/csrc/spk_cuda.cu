@@ -188,7 +188,7 @@ int build_tensor_map(spk_cuda_handle *h) {
   h->stream_ok = (r == CUDA_SUCCESS);
   h->tmap8_ok = false;
   if (h->stream_ok && h->d.lattice == SPK_SC_26N && neigh_like(h->d.model) && h->pk16) {
-    cuuint32_t box8[3] = {(cuuint32_t)ST_BX, (cuuint32_t)StreamCfgOf<SPK_SC_26N, true>::RP, 1};
+    cuuint32_t box8[3] = {(cuuint32_t)ST_BX, (cuuint32_t)StreamCfgOf<SPK_SC_26N, 1>::RP, 1};
     r = ((encode_fn)fn)(&h->tmap8, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, h->base, dims, strides, box8, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -374,13 +374,18 @@ __global__ void __launch_bounds__(256) edge_pair_kernel(const __grid_constant__ 
 #ifndef ST_ADAPT_MINB
 #define ST_ADAPT_MINB 3
 #endif
-template <int LAT, bool ADAPT> using StreamCfgOf = StreamCfg<LAT, ADAPT ? 8 : ST_CR>;
+// NBV (sc/26n candidate-list apps with packed spins): 0 = all-pairs chain on 16-row tiles, 2 CTAs
+// per SM; 1 = candidate elimination on 8-row tiles, 3 CTAs per SM.  (The chain on 8-row tiles with
+// 3 / 4 CTAs per SM measured 40.3 / 33.6 against 41.8 Gsites/s: it is bound by ALU issue, not latency.)
+template <int LAT, int NBV> using StreamCfgOf = StreamCfg<LAT, NBV ? 8 : ST_CR>;
+constexpr int stream_min_blocks(int nbv) { return nbv == 1 ? ST_ADAPT_MINB : 2; }
 
-template <int LAT, int MODEL, bool ONEPASS, bool P16, bool PAIR = false, bool ADAPT = false>
-__global__ void __launch_bounds__(256, ADAPT ? ST_ADAPT_MINB : 2)
+template <int LAT, int MODEL, bool ONEPASS, bool P16, bool PAIR = false, int NBV = 0>
+__global__ void __launch_bounds__(256, stream_min_blocks(NBV))
 sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ SweepArgs a,
                     const __grid_constant__ StreamMap sm) {
-  using C = StreamCfgOf<LAT, ADAPT>;
+  constexpr bool ADAPT = NBV == 1;
+  using C = StreamCfgOf<LAT, NBV>;
   constexpr int TPW = C::CR / 8;  // class rows per warp
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + C::BAR_OFF);
