@@ -120,6 +120,11 @@ int spk_cuda_reset_counters(spk_cuda_handle *h);
  * (SPK_CUDA_NEIGH_MODE=chain|adaptive|auto, default auto); results are bit-identical either way. */
 int spk_cuda_neigh_variant(spk_cuda_handle *h, int *variant, double *mean_distinct);
 
+/* order-independent 64-bit digest of the owned spins keyed on the GLOBAL site index (the slabs'
+ * digests add up, mod 2^64, to the whole lattice's): compares runs at sizes where no host copy
+ * is wanted (tests/test_full_size.py: tuned kernels against the reference-pinned generic kernel) */
+int spk_cuda_digest(spk_cuda_handle *h, uint64_t *digest);
+
 /* diag_style energy (src/diag_energy.cpp:53-66): sum of site_energy over owned sites */
 int spk_cuda_energy(spk_cuda_handle *h, double *energy);
 
@@ -154,6 +159,10 @@ int spk_cuda_halo_mode(const spk_cuda_handle *h);
 int spk_cuda_sync(spk_cuda_handle *h);
 int spk_cuda_timer_start(spk_cuda_handle *h);
 int spk_cuda_timer_stop(spk_cuda_handle *h, float *milliseconds);
+/* lap events between timer_start and timer_stop (bench.py: per-sweep device times of every rank);
+ * timer_laps returns the time from the previous lap (or the start) to each lap */
+int spk_cuda_timer_lap(spk_cuda_handle *h);
+int spk_cuda_timer_laps(spk_cuda_handle *h, float *milliseconds, int capacity, int *nlaps);
 /* number of kernels this handle has launched since create (bench.py's gpu_launches) */
 int spk_cuda_launch_count(spk_cuda_handle *h, int64_t *launches);
 /* raw device pointer to the first owned site (row-major, reference order) for zero-copy hosts */

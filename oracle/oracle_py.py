@@ -72,6 +72,10 @@ def lib():
         L.orc_halfsweep_injected.argtypes = [C.c_void_p, i32p, C.c_int, ip, dp, dp]
         L.orc_halfsweep_philox.restype = C.c_int64
         L.orc_halfsweep_philox.argtypes = [C.c_void_p, i32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, ip]
+        L.orc_halfsweep_philox_double.restype = C.c_int64
+        L.orc_halfsweep_philox_double.argtypes = [C.c_void_p, i32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, ip]
+        L.orc_site_event_words.argtypes = [C.c_void_p, i32p, C.c_int64, C.c_uint32, C.c_uint32]
+        L.orc_site_event_words_double.argtypes = [C.c_void_p, i32p, C.c_int64, C.c_uint32, C.c_uint32]
         L.orc_sweeps_strict.restype = C.c_int64
         L.orc_sweeps_strict.argtypes = [C.c_void_p, i32p, i32p, C.c_int]
         L.orc_strict_siteseeds.argtypes = [C.c_void_p, C.POINTER(Mars), i32p]
@@ -174,6 +178,13 @@ class Oracle:
 
     def halfsweep_philox(self, spin, seed, sweep, color, iloop=0, box=None):
         return self.L.orc_halfsweep_philox(self.ctx, _i32(spin), seed, sweep, color, iloop, _box(box))
+
+    def halfsweep_philox_double(self, spin, seed, sweep, color, iloop=0, box=None):
+        return self.L.orc_halfsweep_philox_double(self.ctx, _i32(spin), seed, sweep, color, iloop, _box(box))
+
+    def site_event_words(self, spin, site, w0, w1, double=False):
+        f = self.L.orc_site_event_words_double if double else self.L.orc_site_event_words
+        return f(self.ctx, _i32(spin), site, w0, w1)
 
     def sweep_philox(self, spin, seed, sweep):
         acc = 0

@@ -410,15 +410,13 @@ uint32_t orc_accept_threshold(double temperature, int dE) {
   return (uint32_t)t;
 }
 
-static int philox_event(const orc_ctx *c, int32_t *spin, int64_t site, uint64_t seed,
-                        uint32_t sweep, int color, int iloop) {
-  const int Q = c->cfg.nspins, nn = c->maxneigh;
-  int old = spin[site];
-  if (c->cfg.model == ORC_POTTS_PIN && old > Q) return 0;
+/* the two Philox words that serve `site` in (sweep, colour, iloop) */
+static void philox_site_words(const orc_ctx *c, int64_t site, uint64_t seed, uint32_t sweep, int color, int iloop,
+                              uint32_t w[2]) {
   int ci, cj, ck, cm;
   site_ijkm(c, site, &ci, &cj, &ck, &cm);
   uint64_t leader;
-  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, blk[4], w[2];
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, blk[4];
   const int isinglike = c->cfg.model == ORC_ISING || c->cfg.model == ORC_ISING_SINGLE;
   if (isinglike) {
     /* ising needs one bit for the trial spin: one block serves the FOUR same-colour sites whose
@@ -436,7 +434,14 @@ static int philox_event(const orc_ctx *c, int32_t *spin, int64_t site, uint64_t 
     const int second = (ci >> 1) & 1;
     w[0] = blk[2 * second]; w[1] = blk[2 * second + 1];
   }
+}
 
+/* One event from two given 32-bit words, integer form (what the CUDA kernels evaluate) */
+int orc_site_event_words(const orc_ctx *c, int32_t *spin, int64_t site, uint32_t w0, uint32_t w1) {
+  const int Q = c->cfg.nspins, nn = c->maxneigh;
+  const uint32_t w[2] = {w0, w1};
+  int old = spin[site];
+  if (c->cfg.model == ORC_POTTS_PIN && old > Q) return 0;
   int64_t nb[ORC_MAXNEIGH];
   orc_neighbors(c, site, nb);
   int e0 = count_unlike(spin, nb, nn, old);
@@ -471,6 +476,40 @@ static int philox_event(const orc_ctx *c, int32_t *spin, int64_t site, uint64_t 
   }
   spin[site] = keep ? trial : old;
   return spin[site] != old;
+}
+
+
+/* The same two words fed as uniforms u = w/2^32 through the reference-pinned DOUBLE formulas of
+ * orc_site_event: the first word is the event's first draw, the second word its second one
+ * (ising/single draws only the acceptance uniform: the second word).  tests/test_oracle_rng.py
+ * checks that this and orc_site_event_words agree, i.e. that the integer reduction stated above
+ * orc_accept_threshold is exact. */
+typedef struct { double u[2]; int n; } word_state;
+static double word_draw(void *p) { word_state *s = (word_state *)p; return s->u[s->n < 1 ? s->n++ : 1]; }
+int orc_site_event_words_double(const orc_ctx *c, int32_t *spin, int64_t site, uint32_t w0, uint32_t w1) {
+  word_state st = {{(double)w0 / 4294967296.0, (double)w1 / 4294967296.0}, 0};
+  if (c->cfg.model == ORC_ISING_SINGLE) st.u[0] = st.u[1];
+  return orc_site_event(c, spin, site, word_draw, &st);
+}
+
+static int philox_event(const orc_ctx *c, int32_t *spin, int64_t site, uint64_t seed,
+                        uint32_t sweep, int color, int iloop) {
+  uint32_t w[2];
+  philox_site_words(c, site, seed, sweep, color, iloop, w);
+  return orc_site_event_words(c, spin, site, w[0], w[1]);
+}
+
+/* the Philox half-sweep evaluated through the double formulas (parity of the integer reduction) */
+int64_t orc_halfsweep_philox_double(const orc_ctx *c, int32_t *spin, uint64_t seed, uint32_t sweep,
+                                    int color, int iloop, const int *box) {
+  int64_t n = orc_nsites(c), acc = 0;
+  for (int64_t s = 0; s < n; s++)
+    if (orc_site_color(c, s) == color && in_box(c, s, box)) {
+      uint32_t w[2];
+      philox_site_words(c, s, seed, sweep, color, iloop, w);
+      acc += orc_site_event_words_double(c, spin, s, w[0], w[1]);
+    }
+  return acc;
 }
 
 int64_t orc_halfsweep_philox(const orc_ctx *c, int32_t *spin, uint64_t seed, uint32_t sweep,

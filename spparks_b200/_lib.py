@@ -24,7 +24,8 @@ SYMBOLS = [
     "spk_cuda_counters", "spk_cuda_reset_counters", "spk_cuda_energy", "spk_cuda_comm_id",
     "spk_cuda_comm_init", "spk_cuda_halo_exchange", "spk_cuda_halo_mode", "spk_cuda_sync", "spk_cuda_timer_start",
     "spk_cuda_timer_stop", "spk_cuda_launch_count", "spk_cuda_device_spins", "spk_cuda_cluster_stats",
-    "spk_cuda_cluster_ids", "spk_cuda_neigh_variant",
+    "spk_cuda_cluster_ids", "spk_cuda_neigh_variant", "spk_cuda_timer_lap", "spk_cuda_timer_laps",
+    "spk_cuda_digest",
 ]
 
 
@@ -84,6 +85,9 @@ def load():
     L.spk_cuda_sync.argtypes = [vp]
     L.spk_cuda_timer_start.argtypes = [vp]
     L.spk_cuda_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.spk_cuda_digest.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.spk_cuda_timer_lap.argtypes = [vp]
+    L.spk_cuda_timer_laps.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     L.spk_cuda_launch_count.argtypes = [vp, i64p]
     L.spk_cuda_device_spins.argtypes = [vp, C.POINTER(vp)]
     _lib = L

@@ -40,6 +40,22 @@ __global__ void __launch_bounds__(256) validate_kernel(const int32_t *__restrict
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(bad, (unsigned long long)c);
 }
 
+// Order-independent 64-bit digest of the owned sites: sum over sites of mix64(global index, spin)
+// (splitmix64 finaliser).  Slabs add up to the digest of the whole lattice, so it compares
+// runs of any decomposition and any kernel family at sizes no host copy is wanted for.
+__global__ void __launch_bounds__(256) digest_kernel(const int32_t *__restrict__ spin, long long n, long long goff,
+                                                     unsigned long long *out) {
+  unsigned long long acc = 0;
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n; s += (long long)gridDim.x * blockDim.x) {
+    unsigned long long z = (unsigned long long)(s + goff) * 0x9E3779B97F4A7C15ull + (unsigned long long)(uint32_t)spin[s];
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    acc += z ^ (z >> 31);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 // diag_style energy (src/diag_energy.cpp:53-66): sum over owned sites of site_energy(i)
 template <int LAT>
 __global__ void __launch_bounds__(256) energy_kernel(const int32_t *__restrict__ spin, Geo g, unsigned long long *out) {

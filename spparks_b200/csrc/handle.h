@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <utility>
+#include <vector>
 
 #include "../../include/spparks_cuda.h"
 #include "sweep_generic.cuh"
@@ -40,6 +41,8 @@ struct spk_cuda_handle {
   EventParams ev;
   cudaStream_t stream = nullptr, comm_stream = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr, ev_halo = nullptr, ev_compute = nullptr;
+  std::vector<cudaEvent_t> laps;  // spk_cuda_timer_lap events since the last timer_start
+  size_t nlaps = 0;
   ncclComm_t comm = nullptr;
   bool tiled = true;  // tuned kernels allowed (SPK_CUDA_FORCE_GENERIC=1 disables, for A/B tests)
   bool use_stream = true;  // SPK_CUDA_NO_STREAM=1 keeps the strip kernel (A/B tests)
@@ -64,7 +67,8 @@ struct spk_cuda_handle {
   unsigned long long *kstat_host = nullptr;  // pinned: [0] copy of *kstat, [1] attempts it covers
   cudaEvent_t ev_kstat = nullptr;
   bool kstat_pending = false;
-  int64_t kstat_attempt0 = 0;    // h->nattempt when the statistic was last reset
+  int64_t nattempt_base = 0;     // attempts before the last spk_cuda_reset_counters
+  int64_t kstat_attempt0 = 0;    // nattempt_base + nattempt when the statistic was last reset
   double kstat_mean = -1.0;      // last mean read back (-1: none yet)
   int32_t *base_alt = nullptr;  // second lattice buffer of the out-of-place fused 2-D sweep
   CUtensorMap tmap_alt;

@@ -215,12 +215,13 @@ int neigh_mode_update(spk_cuda_handle *h) {
     }
   }
   cudaGetLastError();  // cudaErrorNotReady of the query is not an error
-  if (!h->kstat_pending && h->nattempt > h->kstat_attempt0) {
+  const int64_t attempts = h->nattempt_base + h->nattempt;  // monotonic (reset_counters moves the base)
+  if (!h->kstat_pending && attempts > h->kstat_attempt0) {
     CU(cudaMemcpyAsync(h->kstat_host, h->kstat, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemsetAsync(h->kstat, 0, sizeof(unsigned long long), h->stream));
     CU(cudaEventRecord(h->ev_kstat, h->stream));
-    h->kstat_host[1] = (unsigned long long)(h->nattempt - h->kstat_attempt0);
-    h->kstat_attempt0 = h->nattempt;
+    h->kstat_host[1] = (unsigned long long)(attempts - h->kstat_attempt0);
+    h->kstat_attempt0 = attempts;
     h->kstat_pending = true;
   }
   return 0;
@@ -473,6 +474,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   cudaFree(h->cl_label); cudaFree(h->cl_size); cudaFree(h->cl_blocksum); cudaFree(h->cl_count);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->base); cudaFree(h->base_alt); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
+  for (cudaEvent_t e : h->laps) cudaEventDestroy(e);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
@@ -827,7 +829,21 @@ int spk_cuda_reset_counters(spk_cuda_handle *h) {
   if (!h) return fail("null handle");
   CU(cudaSetDevice(h->d.device));
   CU(cudaMemsetAsync(h->naccept, 0, sizeof(unsigned long long), h->stream));
+  h->nattempt_base += h->nattempt;
   h->nattempt = 0;
+  return 0;
+}
+
+int spk_cuda_digest(spk_cuda_handle *h, uint64_t *digest) {
+  if (!h || !digest) return fail("null argument");
+  CU(cudaSetDevice(h->d.device));
+  CU(cudaMemsetAsync(h->escratch, 0, sizeof(unsigned long long), h->stream));
+  digest_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, (long long)h->g.g0 * h->plane, h->escratch);
+  h->launches++;
+  unsigned long long d = 0;
+  CU(cudaMemcpyAsync(&d, h->escratch, sizeof d, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *digest = d;
   return 0;
 }
 
@@ -1057,7 +1073,33 @@ int spk_cuda_sync(spk_cuda_handle *h) {
 int spk_cuda_timer_start(spk_cuda_handle *h) {
   if (!h) return fail("null handle");
   CU(cudaSetDevice(h->d.device));
+  h->nlaps = 0;
   CU(cudaEventRecord(h->t0, h->stream));
+  return 0;
+}
+
+int spk_cuda_timer_lap(spk_cuda_handle *h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->d.device));
+  if (h->nlaps == h->laps.size()) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    h->laps.push_back(e);
+  }
+  CU(cudaEventRecord(h->laps[h->nlaps++], h->stream));
+  return 0;
+}
+
+int spk_cuda_timer_laps(spk_cuda_handle *h, float *milliseconds, int capacity, int *nlaps) {
+  if (!h || !nlaps) return fail("null argument");
+  CU(cudaSetDevice(h->d.device));
+  *nlaps = (int)h->nlaps;
+  cudaEvent_t prev = h->t0;
+  for (size_t i = 0; i < h->nlaps && (int)i < capacity && milliseconds; i++) {
+    CU(cudaEventSynchronize(h->laps[i]));
+    CU(cudaEventElapsedTime(&milliseconds[i], prev, h->laps[i]));
+    prev = h->laps[i];
+  }
   return 0;
 }
 

@@ -150,6 +150,12 @@ class LatticeSweep:
         """0 = single GPU, 1 = NCCL exchange per colour step, 2 = peer-memory stores (no exchange)."""
         return int(self.L.spk_cuda_halo_mode(self.h))
 
+    def digest(self):
+        """Order-independent 64-bit digest of the owned spins (global site index, value)."""
+        d = C.c_uint64()
+        _lib.check(self.L.spk_cuda_digest(self.h, C.byref(d)))
+        return d.value
+
     def neigh_variant(self, with_mean=False):
         """Candidate-list apps on sc/26n: "chain" | "adaptive" (None when not applicable)."""
         v, m = C.c_int(), C.c_double()
@@ -168,6 +174,17 @@ class LatticeSweep:
         ms = C.c_float()
         _lib.check(self.L.spk_cuda_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def timer_lap(self):
+        _lib.check(self.L.spk_cuda_timer_lap(self.h))
+
+    def timer_laps(self):
+        """Device times (ms) between consecutive laps since timer_start."""
+        n = C.c_int()
+        _lib.check(self.L.spk_cuda_timer_laps(self.h, None, 0, C.byref(n)))
+        buf = (C.c_float * max(n.value, 1))()
+        _lib.check(self.L.spk_cuda_timer_laps(self.h, buf, n.value, C.byref(n)))
+        return [float(buf[i]) for i in range(n.value)]
 
     def launch_count(self):
         n = C.c_int64()

@@ -58,3 +58,41 @@ def test_uniform_lattice_is_a_fixed_point_at_full_size():
         assert s.energy() == 0.0 and s.counters() == (0, 2 * L ** 3)
         assert s.cluster_stats()[0] == 1
         s.close()
+
+
+@pytest.mark.parametrize("model,lat,n,q,T,pin", [
+    ("ising", "sq/4n", (16384, 16384, 1), 2, 1.1346, 0.0),               # configs[1]
+    ("potts/neighonly", "sc/26n", (1024, 1024, 1024), 10000, 0.5, 0.0),   # configs[2]
+    ("potts/pin", "sc/26n", (1024, 1024, 1024), 10000, 0.5, 0.01),        # configs[3], one GPU's share
+    ("potts", "tri", (32768, 16384, 1), 1000, 0.5, 0.0),                  # configs[4]
+], ids=["ising-16384sq", "neighonly-1024cube", "pin-1024cube", "potts-tri-32768"])
+def test_tuned_kernels_equal_generic_kernel_at_full_size(model, lat, n, q, T, pin, monkeypatch):
+    """The generic kernel is pinned to the reference's fixtures and runs at any size; the tuned
+    kernels (TMA streaming / colour-fused tiles, both first-occurrence variants of the
+    candidate-list apps) must reproduce it bit for bit at the BASELINE sizes: a 64-bit digest of
+    (site, spin) over the whole lattice, the counters and the energy after every sweep."""
+    from spparks_b200 import LatticeSweep
+    if _free_gb() < 40:
+        pytest.skip("needs 40 GB of free device memory")
+
+    def run(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s = LatticeSweep(model, lat, n[0], n[1], n[2], nspins=q, temperature=T, seed=31337)
+        for k in env:
+            monkeypatch.delenv(k)
+        s.randomize(11, 1, 2 if model == "ising" else q)
+        if pin:
+            s.pin_random(5, pin)
+        out = [s.digest()]
+        for sw in range(2):
+            s.sweeps(sw, 1)
+            out.append((s.digest(), s.counters(), s.energy()))
+        s.close()
+        return out
+
+    want = run({"SPK_CUDA_FORCE_GENERIC": "1"})
+    assert run({}) == want
+    if model == "potts/neighonly":
+        assert run({"SPK_CUDA_NEIGH_MODE": "adaptive"}) == want
+        assert run({"SPK_CUDA_NEIGH_MODE": "chain"}) == want
