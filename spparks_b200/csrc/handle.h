@@ -67,6 +67,7 @@ struct spk_cuda_handle {
   unsigned long long *kstat_host = nullptr;  // pinned: [0] copy of *kstat, [1] attempts it covers
   cudaEvent_t ev_kstat = nullptr;
   bool kstat_pending = false;
+  bool kstat_discard = false;    // the pending read-back belongs to a lattice that has been replaced
   int64_t nattempt_base = 0;     // attempts before the last spk_cuda_reset_counters
   int64_t kstat_attempt0 = 0;    // nattempt_base + nattempt when the statistic was last reset
   double kstat_mean = -1.0;      // last mean read back (-1: none yet)

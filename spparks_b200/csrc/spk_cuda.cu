@@ -202,11 +202,22 @@ int build_tensor_map(spk_cuda_handle *h) {
 // the mean nevent the kernels accumulate in h->kstat.  Called at the first colour of a sweep;
 // never blocks: the statistic is copied to pinned memory behind the launches already queued and
 // picked up one or two sweeps later.  Both variants give identical spins, only the speed differs.
+// the spins were replaced (upload, randomize): forget what the statistic said about the old lattice
+void neigh_mode_reset(spk_cuda_handle *h) {
+  if (!h->kstat || h->neigh_mode != 2) return;
+  h->neigh_adaptive = false;
+  h->kstat_mean = -1.0;
+  h->kstat_discard = h->kstat_pending;
+  cudaMemsetAsync(h->kstat, 0, sizeof(unsigned long long), h->stream);
+  h->kstat_attempt0 = h->nattempt_base + h->nattempt;
+}
+
 int neigh_mode_update(spk_cuda_handle *h) {
   if (!h->kstat || h->neigh_mode != 2) return 0;
   if (h->kstat_pending && cudaEventQuery(h->ev_kstat) == cudaSuccess) {
     h->kstat_pending = false;
-    if (h->kstat_host[1] > 0) {
+    if (h->kstat_discard) h->kstat_discard = false;  // measured on a lattice that has been replaced since
+    else if (h->kstat_host[1] > 0) {
       h->kstat_mean = (double)h->kstat_host[0] / (double)h->kstat_host[1];
       // hysteresis around the measured break-even (SPK_CUDA_NEIGH_SWITCH, distinct values per site)
       static const double sw = [] { const char *e = getenv("SPK_CUDA_NEIGH_SWITCH"); const double v = e ? atof(e) : 0.0; return v > 0.0 ? v : 2.9; }();
@@ -494,6 +505,7 @@ int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n) {
   CU(cudaSetDevice(h->d.device));
   CU(cudaMemcpyAsync(h->spin, host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   h->ghosts_valid = false;
+  neigh_mode_reset(h);
   // the reference's init_app refuses spins outside 1..Q (Q+1 = pinned for potts/pin); the kernels
   // rely on it (packed 16-bit compares), so the check is repeated where the spins enter the device
   const int hi = ising_like(h->d.model) ? 2 : h->d.nspins + (h->d.model == SPK_POTTS_PIN ? 1 : 0);
@@ -533,6 +545,7 @@ int spk_cuda_randomize(spk_cuda_handle *h, uint64_t seed, int32_t lo, int32_t hi
   const int64_t goff = (int64_t)h->g.g0 * h->plane;
   randomize_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, goff, seed, lo, (uint32_t)(hi - lo + 1));
   h->ghosts_valid = false;
+  neigh_mode_reset(h);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
