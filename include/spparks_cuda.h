@@ -22,6 +22,7 @@
 #ifndef SPPARKS_CUDA_H
 #define SPPARKS_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -99,6 +100,18 @@ int spk_cuda_set_siteseeds(spk_cuda_handle *h, const int32_t *seeds, int64_t n);
 int spk_cuda_get_siteseeds(spk_cuda_handle *h, int32_t *seeds, int64_t n);
 int spk_cuda_sweep_color_strict(spk_cuda_handle *h, int color, const int32_t *box, int nloop);
 
+/* `sweep ... mask yes` (src/app_lattice.cpp:258-267, 784-792, 809-819): one mask byte per site on
+ * the device, zeroed when enabled.  While enabled, every sweep entry point skips masked sites and
+ * the events update the masks as the reference's do (src/app_potts.cpp:136-146: mask the site if
+ * einitial < numneigh/2, unmask all neighbours of a changed site); the sweeps then run through
+ * the generic kernel.  mask_clear_border is AppLattice::boundary_clear_mask (:655, :1158-1164) for
+ * the loop set the caller is about to sweep: color = 0 -> the set is the sector `box` (NULL =
+ * whole slab), its border sites are unmasked; color = 1..ncolors -> the set is that colour class
+ * inside `box`, all of it border.  download_mask copies the owned sites' mask bytes (tests). */
+int spk_cuda_mask_enable(spk_cuda_handle *h, int on);
+int spk_cuda_mask_clear_border(spk_cuda_handle *h, const int32_t *box, int color);
+int spk_cuda_download_mask(spk_cuda_handle *h, unsigned char *host, int64_t n);
+
 /* nsweeps full sweeps of iterate_rejection with `sweep color`, `sector no`
  * (src/app_lattice.cpp:646-705): for each sweep, for each colour 1..ncolors: ghost refresh
  * (comm->all(), src/app_lattice.cpp:650-651) then the colour kernel.  Sweep numbers
@@ -165,6 +178,11 @@ int spk_cuda_timer_lap(spk_cuda_handle *h);
 int spk_cuda_timer_laps(spk_cuda_handle *h, float *milliseconds, int capacity, int *nlaps);
 /* number of kernels this handle has launched since create (bench.py's gpu_launches) */
 int spk_cuda_launch_count(spk_cuda_handle *h, int64_t *launches);
+/* page-lock / release a host array that spk_cuda_upload_spins / _download_spins will be called
+ * with repeatedly (the plugin does it for iarray[0], re-registering in grow_app when
+ * Memory::grow moves it, src/app_potts.cpp:68-71): copies then run at full PCIe speed */
+int spk_cuda_host_register(void *ptr, size_t bytes);
+int spk_cuda_host_unregister(void *ptr);
 /* raw device pointer to the first owned site (row-major, reference order) for zero-copy hosts */
 int spk_cuda_device_spins(spk_cuda_handle *h, void **dptr);
 

@@ -76,6 +76,11 @@ def lib():
         L.orc_halfsweep_philox_double.argtypes = [C.c_void_p, i32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, ip]
         L.orc_site_event_words.argtypes = [C.c_void_p, i32p, C.c_int64, C.c_uint32, C.c_uint32]
         L.orc_site_event_words_double.argtypes = [C.c_void_p, i32p, C.c_int64, C.c_uint32, C.c_uint32]
+        L.orc_boundary_clear_mask.argtypes = [C.c_void_p, C.c_void_p, ip]
+        L.orc_halfsweep_injected_mask.restype = C.c_int64
+        L.orc_halfsweep_injected_mask.argtypes = [C.c_void_p, i32p, C.c_void_p, C.c_int, ip, dp, dp]
+        L.orc_halfsweep_philox_mask.restype = C.c_int64
+        L.orc_halfsweep_philox_mask.argtypes = [C.c_void_p, i32p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, ip]
         L.orc_sweeps_strict.restype = C.c_int64
         L.orc_sweeps_strict.argtypes = [C.c_void_p, i32p, i32p, C.c_int]
         L.orc_strict_siteseeds.argtypes = [C.c_void_p, C.POINTER(Mars), i32p]
@@ -175,6 +180,18 @@ class Oracle:
 
     def halfsweep_injected(self, spin, color, u1, u2, box=None):
         return self.L.orc_halfsweep_injected(self.ctx, _i32(spin), color, _box(box), _f64(u1), _f64(u2))
+
+    def boundary_clear_mask(self, mask, box):
+        assert mask.dtype == np.uint8 and mask.flags.c_contiguous
+        self.L.orc_boundary_clear_mask(self.ctx, mask.ctypes.data, _box(box))
+
+    def halfsweep_injected_mask(self, spin, mask, color, u1, u2, box=None):
+        assert mask.dtype == np.uint8 and mask.flags.c_contiguous
+        return self.L.orc_halfsweep_injected_mask(self.ctx, _i32(spin), mask.ctypes.data, color, _box(box), _f64(u1), _f64(u2))
+
+    def halfsweep_philox_mask(self, spin, mask, seed, sweep, color, iloop=0, box=None):
+        assert mask.dtype == np.uint8 and mask.flags.c_contiguous
+        return self.L.orc_halfsweep_philox_mask(self.ctx, _i32(spin), mask.ctypes.data, seed, sweep, color, iloop, _box(box))
 
     def halfsweep_philox(self, spin, seed, sweep, color, iloop=0, box=None):
         return self.L.orc_halfsweep_philox(self.ctx, _i32(spin), seed, sweep, color, iloop, _box(box))

@@ -20,6 +20,12 @@
 //        kfile = raw int32[nlocal], k_i in [1, 2^31-2].
 //   @setsweep <kfile>         one pass over the sets in AppLattice::iterate_rejection order
 //        (src/app_lattice.cpp:646-699: sectors -> colours -> sites, nloop=1), injected the same way
+//   @masksweep <kfile> <maskfile>
+//        one pass of iterate_rejection with `sweep color mask yes` (src/app_lattice.cpp:646-699):
+//        per loop set the reference's own boundary_clear_mask(iset) (:655, :1158), then
+//        sweep_mask_nostrict's rule `if (mask[i]) continue;` (:784-792) around the same injected
+//        site_event_rejection calls as @setsweep (the mask updates are inside the reference's
+//        events).  Afterwards the mask bytes of the owned sites are written to maskfile (int32 each).
 //   @energy                   prints  "energy <sum_i site_energy(i)>"       (src/diag_energy.cpp:53-66)
 //   @counters                 prints  "counters <naccept> <nattempt> <nsweeps>"
 //   @time <label>             prints wall seconds since the previous @time
@@ -62,6 +68,9 @@ struct Peek : public AppLattice {
   using AppLattice::bothflag;
   using AppLattice::siteseeds;
   using AppLattice::Set;
+  using AppLattice::Lmask;
+  using AppLattice::mask;
+  using AppLattice::boundary_clear_mask;
 };
 
 template <class T> T &peek(AppLattice *al, T AppLattice::*m) { return al->*m; }
@@ -177,6 +186,29 @@ int main(int argc, char **argv) {
           }
         }
       }
+    } else if (!strcmp(cmd, "@masksweep")) {
+      std::vector<int> k = read_ints(s1, nlocal);
+      Peek::Set *set = peek(al, &Peek::set);
+      int nset = peek(al, &Peek::nset), nsector = peek(al, &Peek::nsector);
+      int ncolors = peek(al, &Peek::ncolors), both = peek(al, &Peek::bothflag);
+      char *mask = peek(al, &Peek::mask);
+      if (!peek(al, &Peek::Lmask) || !mask) { fprintf(stderr, "ref_driver: @masksweep needs sweep ... mask yes + run\n"); return 2; }
+      void (AppLattice::*clear)(int) = &Peek::boundary_clear_mask;
+      int nset_loop = both ? nsector : nset;
+      for (int iset = 0; iset < nset_loop; iset++) {
+        (al->*clear)(iset);
+        for (int ic = 0; ic < (both ? ncolors : 1); ic++) {
+          int jset = both ? nsector + iset * ncolors + ic : iset;
+          for (int m = 0; m < set[jset].nlocal; m++) {
+            int i = set[jset].site2i[m];
+            if (mask[i]) continue;
+            inject_event(al, i, k[al->id[i] - 1]);
+          }
+        }
+      }
+      std::vector<int> mv(nlocal);
+      for (int i = 0; i < nlocal; i++) mv[al->id[i] - 1] = mask[i];
+      write_ints(s2, mv.data(), nlocal);
     } else if (!strcmp(cmd, "@energy")) {
       double e = 0.0;
       for (int i = 0; i < nlocal; i++) e += al->site_energy(i);

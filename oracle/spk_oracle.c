@@ -311,7 +311,12 @@ static int count_unlike(const int32_t *spin, const int64_t *nb, int nn, int valu
   return e;
 }
 
+static int site_event_mask(const orc_ctx *c, int32_t *spin, unsigned char *mask, int64_t site, orc_draw_fn draw, void *state);
 int orc_site_event(const orc_ctx *c, int32_t *spin, int64_t site, orc_draw_fn draw, void *state) {
+  return site_event_mask(c, spin, NULL, site, draw, state);
+}
+
+static int site_event_mask(const orc_ctx *c, int32_t *spin, unsigned char *mask, int64_t site, orc_draw_fn draw, void *state) {
   /* AppIsing (src/app_ising.cpp:104-136), AppPotts (src/app_potts.cpp:112-146),
    * AppPottsNeighOnly (src/app_potts_neighonly.cpp:71-117), AppPottsPin
    * (src/app_potts_pin.cpp:93-131) ::site_event_rejection, masks off */
@@ -364,6 +369,14 @@ int orc_site_event(const orc_ctx *c, int32_t *spin, int64_t site, orc_draw_fn dr
     }
   }
   spin[site] = keep ? trial : old;
+  /* `sweep ... mask yes` (src/app_potts.cpp:136-146 and the same lines of the other apps): reached
+   * only when the event ran to its end — the early returns above (pinned site, no candidate, null
+   * bin) leave the masks alone, as in the reference */
+  if (mask) {
+    if (2 * e0 < nn) mask[site] = 1; /* einitial < 0.5*numneigh[i] */
+    if (spin[site] != old)
+      for (int n = 0; n < nn; n++) mask[nb[n]] = 0;
+  }
   return spin[site] != old;
 }
 
@@ -389,6 +402,31 @@ int64_t orc_halfsweep_injected(const orc_ctx *c, int32_t *spin, int color, const
     double u[2] = {u1[s], u2[s]};
     inj_state st = {u, 0};
     acc += orc_site_event(c, spin, s, inj_draw, &st);
+  }
+  return acc;
+}
+
+/* AppLattice::boundary_clear_mask (src/app_lattice.cpp:1158-1164) for the set `box`: border =
+ * sites of the set with a neighbour outside it (find_border_sites, :1092-1148, one layer) */
+void orc_boundary_clear_mask(const orc_ctx *c, unsigned char *mask, const int *box) {
+  int64_t n = orc_nsites(c), nb[ORC_MAXNEIGH];
+  for (int64_t s = 0; s < n; s++) {
+    if (!in_box(c, s, box)) continue;
+    orc_neighbors(c, s, nb);
+    for (int q = 0; q < c->maxneigh; q++)
+      if (!in_box(c, nb[q], box)) { mask[s] = 0; break; }
+  }
+}
+
+/* sweep_mask_nostrict over one colour set (src/app_lattice.cpp:784-792), injected uniforms */
+int64_t orc_halfsweep_injected_mask(const orc_ctx *c, int32_t *spin, unsigned char *mask, int color, const int *box,
+                                    const double *u1, const double *u2) {
+  int64_t n = orc_nsites(c), acc = 0;
+  for (int64_t s = 0; s < n; s++) {
+    if (orc_site_color(c, s) != color || !in_box(c, s, box) || mask[s]) continue;
+    double u[2] = {u1[s], u2[s]};
+    inj_state st = {u, 0};
+    acc += site_event_mask(c, spin, mask, s, inj_draw, &st);
   }
   return acc;
 }
@@ -437,7 +475,11 @@ static void philox_site_words(const orc_ctx *c, int64_t site, uint64_t seed, uin
 }
 
 /* One event from two given 32-bit words, integer form (what the CUDA kernels evaluate) */
+static int words_event_mask(const orc_ctx *c, int32_t *spin, unsigned char *mask, int64_t site, uint32_t w0, uint32_t w1);
 int orc_site_event_words(const orc_ctx *c, int32_t *spin, int64_t site, uint32_t w0, uint32_t w1) {
+  return words_event_mask(c, spin, NULL, site, w0, w1);
+}
+static int words_event_mask(const orc_ctx *c, int32_t *spin, unsigned char *mask, int64_t site, uint32_t w0, uint32_t w1) {
   const int Q = c->cfg.nspins, nn = c->maxneigh;
   const uint32_t w[2] = {w0, w1};
   int old = spin[site];
@@ -475,6 +517,11 @@ int orc_site_event_words(const orc_ctx *c, int32_t *spin, int64_t site, uint32_t
     else if (w[1] > orc_accept_threshold(c->cfg.temperature, e1 - e0)) keep = 0;
   }
   spin[site] = keep ? trial : old;
+  if (mask) { /* as in site_event_mask */
+    if (2 * e0 < nn) mask[site] = 1;
+    if (spin[site] != old)
+      for (int n = 0; n < nn; n++) mask[nb[n]] = 0;
+  }
   return spin[site] != old;
 }
 
@@ -497,6 +544,19 @@ static int philox_event(const orc_ctx *c, int32_t *spin, int64_t site, uint64_t 
   uint32_t w[2];
   philox_site_words(c, site, seed, sweep, color, iloop, w);
   return orc_site_event_words(c, spin, site, w[0], w[1]);
+}
+
+/* sweep_mask_nostrict over one colour set in Philox mode */
+int64_t orc_halfsweep_philox_mask(const orc_ctx *c, int32_t *spin, unsigned char *mask, uint64_t seed, uint32_t sweep,
+                                  int color, int iloop, const int *box) {
+  int64_t n = orc_nsites(c), acc = 0;
+  for (int64_t s = 0; s < n; s++)
+    if (orc_site_color(c, s) == color && in_box(c, s, box) && !mask[s]) {
+      uint32_t w[2];
+      philox_site_words(c, s, seed, sweep, color, iloop, w);
+      acc += words_event_mask(c, spin, mask, s, w[0], w[1]);
+    }
+  return acc;
 }
 
 /* the Philox half-sweep evaluated through the double formulas (parity of the integer reduction) */

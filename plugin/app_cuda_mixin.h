@@ -57,8 +57,13 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       nspins_cuda = this->nspins;
     }
     this->allow_kmc = 0;          // the device path is rejection KMC only
-    this->allow_masking = 0;
+    this->allow_masking = 1;      // `sweep ... mask yes`: mask bytes live on the device
     handle = NULL;
+    host_sync = 1;
+    pinned = NULL;
+    pinned_bytes = 0;
+    perf_sites = 0;
+    perf_seconds = 0.0;
     device = 0;
     seed_set = 0;
     seed = 0;
@@ -67,7 +72,11 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     device_current = 0;
   }
 
-  virtual ~AppCudaMixin() { if (handle) spk_cuda_destroy(handle); }
+  virtual ~AppCudaMixin()
+  {
+    if (pinned) spk_cuda_host_unregister(pinned);
+    if (handle) spk_cuda_destroy(handle);
+  }
 
   void input_app(char *command, int narg, char **arg)
   {
@@ -78,7 +87,27 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       if (narg != 1) this->error->all(FLERR,"Illegal cuda_seed command");
       seed = strtoull(arg[0],NULL,10);
       seed_set = 1;
+    } else if (strcmp(command,"cuda_host_sync") == 0) {
+      // yes (default): iarray[0] is refreshed before every Output::compute, as host-side
+      //   diagnostics and dumps expect
+      // no: the user asserts that nothing reads the host spins during a run (only /cuda
+      //   diagnostics and the stats line are active); the lattice comes back when the run ends
+      if (narg != 1) this->error->all(FLERR,"Illegal cuda_host_sync command");
+      if (strcmp(arg[0],"yes") == 0) host_sync = 1;
+      else if (strcmp(arg[0],"no") == 0) host_sync = 0;
+      else this->error->all(FLERR,"Illegal cuda_host_sync command");
     } else Base::input_app(command,narg,arg);
+  }
+
+  // per-site arrays may have moved (Memory::grow): the pinned registration follows iarray[0]
+
+  void grow_app()
+  {
+    Base::grow_app();
+    if (pinned && pinned != (void *) this->iarray[0]) {
+      spk_cuda_host_unregister(pinned);
+      pinned = NULL;
+    }
   }
 
   void init_app()
@@ -130,6 +159,21 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     desc.rank = this->me;
     desc.nranks = this->nprocs;
     check(spk_cuda_create(&desc,&handle));
+    if (this->Lmask) check(spk_cuda_mask_enable(handle,1));   // src/app_lattice.cpp:258-267
+
+    // tri with an odd number of rows: the two basis sites of the middle row fall into different
+    // sectors (y = (j+1/2)*sqrt(3) vs ymid, src/app_lattice.cpp:959-974): not a box of cells
+    if (lat == SPK_TRI && this->nsector >= 4 && (slab_hi()-slab_lo()) % 2)
+      this->error->all(FLERR,"app_style */cuda: sectors in y need an even number of tri rows per processor");
+
+    // page-lock the host spins once: uploads / downloads then run at full PCIe speed
+    if (!pinned && this->nlocal > 0) {
+      size_t bytes = (size_t) this->nlocal * sizeof(int);
+      if (spk_cuda_host_register(this->iarray[0],bytes) == 0) {
+        pinned = this->iarray[0];
+        pinned_bytes = bytes;
+      }
+    }
     device_current = 0;      // the host copy (create_sites, set, pin, a previous run) is the only one
     if (spk_cuda_nlocal(handle) != this->nlocal)
       this->error->one(FLERR,"app_style */cuda: slab size does not match nlocal");
@@ -149,7 +193,6 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     // same enum as src/app_lattice.cpp:40 (file-local there)
     enum{NOSWEEP,RANDOM,RASTER,COLOR,COLOR_STRICT};
 
-    if (this->Lmask) this->error->all(FLERR,"Mask logic not implemented in app");
     int lat = this->domain->lattice->style;
     int ncolor = spk_cuda_ncolors(lat);
     int strict = (this->sweepflag == COLOR_STRICT);
@@ -181,17 +224,31 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     for (int icolor = 0; whole && icolor < ncolor; icolor++)
       if (set_nloop(0,icolor,ncolor) != 1) whole = 0;
 
+    // the reference's loop sets: sectors (bothflag, or sweep random/raster run as colours), else
+    // the colour sets themselves; boundary_clear_mask acts on the loop set (src/app_lattice.cpp:655)
+    int sets_are_sectors = !(this->sweepflag == COLOR || this->sweepflag == COLOR_STRICT) || this->bothflag;
+
+    double t_start = MPI_Wtime();
+    bigint sweeps_start = this->nsweeps;
     int done = 0;
     while (!done) {
       this->timer->stamp();
-      if (whole) check(spk_cuda_sweeps(handle,sweep_counter,1));
+      if (whole) check(spk_cuda_sweeps(handle,sweep_counter,1));   // (masks: handled per colour set inside)
       else for (int isector = 0; isector < nsector; isector++) {
         int box[6];
         sector_box(isector,nsector,box);
+        if (this->Lmask && sets_are_sectors)
+          check(spk_cuda_mask_clear_border(handle,nsector > 1 ? box : NULL,0));
         for (int icolor = 0; icolor < ncolor; icolor++) {
           int nloop = set_nloop(isector,icolor,ncolor);
           if (nloop < 1) continue;
-          check(spk_cuda_halo_exchange(handle));      // comm->all(), src/app_lattice.cpp:650-651
+          if (this->nprocs > 1) {
+            this->timer->stamp(TIME_SOLVE);
+            check(spk_cuda_halo_exchange(handle));      // comm->all(), src/app_lattice.cpp:648-652
+            this->timer->stamp(TIME_COMM);
+          }
+          if (this->Lmask && !sets_are_sectors)
+            check(spk_cuda_mask_clear_border(handle,NULL,icolor+1));
           if (strict)
             check(spk_cuda_sweep_color_strict(handle,icolor+1,nsector > 1 ? box : NULL,nloop));
           else
@@ -204,8 +261,10 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       if (this->time >= stoptime) done = 1;
 
       if (done || this->time >= this->nextoutput) {
-        // host copy must be current before diagnostics, stats and dumps read it
-        check(spk_cuda_download_spins(handle,this->iarray[0],this->nlocal));
+        // host copy must be current before host-side diagnostics and dumps read it
+        // (cuda_host_sync no: only when the run ends)
+        if (host_sync || done)
+          check(spk_cuda_download_spins(handle,this->iarray[0],this->nlocal));
         int64_t acc,att;
         check(spk_cuda_counters(handle,&acc,&att));
         this->naccept = naccept0 + acc;
@@ -216,6 +275,21 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       }
     }
     if (strict) check(spk_cuda_get_siteseeds(handle,this->siteseeds,this->nlocal));
+
+    // throughput of this run's sweep loop (uploads, downloads and output included), next to
+    // the reference's own timing breakdown (src/finish.cpp:30-129)
+    perf_seconds += MPI_Wtime() - t_start;
+    perf_sites += (double) (this->nsweeps - sweeps_start) * (double) this->nglobal;
+    if (this->me == 0 && perf_seconds > 0.0) {
+      double gs = perf_sites/perf_seconds*1.0e-9;
+      double bytes = 4.0*(ncolor+1);
+      char line[256];
+      snprintf(line,sizeof line,"CUDA sweep loop: %.4g site-updates in %.4g s = %.4g Gsites/s "
+               "(%.4g GB/s of algorithmic lattice traffic at %g bytes/site-update)\n",
+               perf_sites,perf_seconds,gs,gs*bytes,bytes);
+      if (this->screen) fputs(line,this->screen);
+      if (this->logfile) fputs(line,this->logfile);
+    }
   }
 
   // SpkCudaHost: the /cuda diagnostics read the device lattice.  Output::compute is only ever
@@ -234,7 +308,22 @@ class AppCudaMixin : public Base, public SpkCudaHost {
 
  private:
   spk_cuda_handle *handle;
-  int device,nspins_cuda,seed_set,warned,device_current;
+  int device,nspins_cuda,seed_set,warned,device_current,host_sync;
+  void *pinned;
+  size_t pinned_bytes;
+  double perf_sites,perf_seconds;
+
+  // this rank's slab of the last dimension in global cells (init_app checked slab index == rank)
+  int slab_lo()
+  {
+    int n = this->domain->dimension == 3 ? this->domain->nz : this->domain->ny;
+    return (int) ((bigint) this->me * n / this->nprocs);
+  }
+  int slab_hi()
+  {
+    int n = this->domain->dimension == 3 ? this->domain->nz : this->domain->ny;
+    return (int) ((bigint) (this->me+1) * n / this->nprocs);
+  }
   uint64_t seed;
   uint32_t sweep_counter;
 
@@ -243,18 +332,25 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     if (rc) this->error->one(FLERR,spk_cuda_last_error());
   }
 
-  // sector of create_set() (src/app_lattice.cpp:969-984) as a box of global cell indices:
-  // x < xmid  <=>  i < ceil(nx/2) for every basis site of the supported lattices
+  // sector of create_set() (src/app_lattice.cpp:959-984) as a box of global cell indices.  The
+  // reference splits at the midpoints of THIS RANK's sub-domain: [0,n) in the undivided
+  // dimensions, the rank's own slab in the last one.  x < xmid  <=>  cell index < ceil((lo+hi)/2)
+  // for every basis site of the supported lattices (tri rows: init_app refuses odd counts).
 
   void sector_box(int isector, int nsector, int *box)
   {
     int nx = this->domain->nx, ny = this->domain->ny, nz = this->domain->nz;
-    box[0] = 0; box[1] = nx; box[2] = 0; box[3] = ny; box[4] = 0; box[5] = nz;
+    int lo[3] = {0,0,0}, hi[3] = {nx,ny,nz};
+    int sd = this->domain->dimension - 1;
+    lo[sd] = slab_lo(); hi[sd] = slab_hi();
+    for (int d = 0; d < 3; d++) { box[2*d] = lo[d]; box[2*d+1] = hi[d]; }
+    if (this->domain->dimension == 2) { box[4] = 0; box[5] = nz; }
     if (nsector == 1) return;
-    int hx = (nx+1)/2, hy = (ny+1)/2, hz = (nz+1)/2;
-    if (isector & 1) box[0] = hx; else box[1] = hx;
-    if (nsector >= 4) { if (isector & 2) box[2] = hy; else box[3] = hy; }
-    if (nsector == 8) { if (isector & 4) box[4] = hz; else box[5] = hz; }
+    int mid[3];
+    for (int d = 0; d < 3; d++) mid[d] = (lo[d]+hi[d]+1)/2;
+    if (isector & 1) box[0] = mid[0]; else box[1] = mid[0];
+    if (nsector >= 4) { if (isector & 2) box[2] = mid[1]; else box[3] = mid[1]; }
+    if (nsector == 8) { if (isector & 4) box[4] = mid[2]; else box[5] = mid[2]; }
   }
 
   // nloop of the reference's set for (sector,colour) (src/app_lattice.cpp:401-410)
@@ -272,8 +368,12 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     iset = isector;
     if (this->sweepflag == RASTER) return this->set[iset].nloop;
     if (this->set[iset].nlocal == 0) return 0;
-    int n = this->set[iset].nselect / this->set[iset].nlocal;
-    return n < 1 ? 1 : n;
+    // dt_rkmc is computed from nselect (src/app_lattice.cpp:385-417): whole passes only, or the
+    // clock and the attempt counters would disagree with the attempts actually made
+    if (this->set[iset].nselect % this->set[iset].nlocal)
+      this->error->all(FLERR,"app_style */cuda runs sweep random as colour sweeps: "
+                       "nstop must give a whole number of attempts per site");
+    return this->set[iset].nselect / this->set[iset].nlocal;
   }
 };
 

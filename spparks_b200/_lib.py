@@ -25,7 +25,8 @@ SYMBOLS = [
     "spk_cuda_comm_init", "spk_cuda_halo_exchange", "spk_cuda_halo_mode", "spk_cuda_sync", "spk_cuda_timer_start",
     "spk_cuda_timer_stop", "spk_cuda_launch_count", "spk_cuda_device_spins", "spk_cuda_cluster_stats",
     "spk_cuda_cluster_ids", "spk_cuda_neigh_variant", "spk_cuda_timer_lap", "spk_cuda_timer_laps",
-    "spk_cuda_digest",
+    "spk_cuda_digest", "spk_cuda_mask_enable", "spk_cuda_mask_clear_border", "spk_cuda_download_mask",
+    "spk_cuda_host_register", "spk_cuda_host_unregister",
 ]
 
 
@@ -85,6 +86,11 @@ def load():
     L.spk_cuda_sync.argtypes = [vp]
     L.spk_cuda_timer_start.argtypes = [vp]
     L.spk_cuda_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.spk_cuda_mask_enable.argtypes = [vp, C.c_int]
+    L.spk_cuda_mask_clear_border.argtypes = [vp, i32p, C.c_int]
+    L.spk_cuda_download_mask.argtypes = [vp, vp, C.c_int64]
+    L.spk_cuda_host_register.argtypes = [vp, C.c_size_t]
+    L.spk_cuda_host_unregister.argtypes = [vp]
     L.spk_cuda_digest.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.spk_cuda_timer_lap.argtypes = [vp]
     L.spk_cuda_timer_laps.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]

@@ -40,6 +40,67 @@ __global__ void __launch_bounds__(256) validate_kernel(const int32_t *__restrict
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(bad, (unsigned long long)c);
 }
 
+// AppLattice::boundary_clear_mask (src/app_lattice.cpp:1158-1164) for a loop set given as a box
+// of local cells: the border sites found by find_border_sites (:1092-1148, one layer since
+// delpropensity + delevent = 1) are the sites of the set with at least one neighbour outside it.
+// color0 >= 0 restricts the set to one colour class (a colour set without sectors): every
+// neighbour of such a site has another colour, so the whole class is border.
+// A neighbour beyond the slab (ghost plane / row of a multi-GPU run) is outside every set.
+template <int LAT>
+__global__ void __launch_bounds__(256) mask_border_kernel(unsigned char *mask, Geo g, Box b, int multi) {
+  using L = Lat<LAT>;
+  constexpr int NN = L::NN, NB = L::NB;
+  const long long ni = b.ihi - b.ilo, nj = b.jhi - b.jlo, nk = b.khi - b.klo;
+  const long long ncell = ni * nj * nk;
+  const long long sy = (long long)g.X * NB, sz = sy * g.Y;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
+    const int i = b.ilo + (int)(c % ni), j = b.jlo + (int)((c / ni) % nj), k = b.klo + (int)(c / (ni * nj));
+#pragma unroll
+    for (int m = 0; m < NB; m++) {
+      bool border = false;
+#pragma unroll
+      for (int n = 0; n < NN; n++) {
+        const Off o = L::off(m, n);
+        int ii = i + o.dx, jj = j + o.dy, kk = k + o.dz;
+        ii = ii < 0 ? ii + g.X : (ii >= g.X ? ii - g.X : ii);  // x is never the slab dimension
+        bool ghost = false;
+        if (L::DIM == 2) {
+          if (jj < 0 || jj >= g.Y) { if (multi) ghost = true; else jj = jj < 0 ? jj + g.Y : jj - g.Y; }
+        } else {
+          jj = jj < 0 ? jj + g.Y : (jj >= g.Y ? jj - g.Y : jj);
+          if (kk < 0 || kk >= g.Z) { if (multi) ghost = true; else kk = kk < 0 ? kk + g.Z : kk - g.Z; }
+        }
+        border |= ghost || ii < b.ilo || ii >= b.ihi || jj < b.jlo || jj >= b.jhi || kk < b.klo || kk >= b.khi;
+      }
+      if (border) mask[k * sz + j * sy + (long long)i * NB + m] = 0;
+    }
+  }
+}
+
+// the sites of colour c0 inside the box (a colour set as loop set: all of it is border)
+template <int LAT>
+__global__ void __launch_bounds__(256) mask_color_clear_kernel(unsigned char *mask, Geo g, Box b, int c0) {
+  using L = Lat<LAT>;
+  constexpr int NB = L::NB;
+  const long long ni = b.ihi - b.ilo, nj = b.jhi - b.jlo, nk = b.khi - b.klo;
+  const long long ncell = ni * nj * nk;
+  const long long sy = (long long)g.X * NB, sz = sy * g.Y;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
+    const int i = b.ilo + (int)(c % ni), j = b.jlo + (int)((c / ni) % nj), k = b.klo + (int)(c / (ni * nj));
+    const int jg = L::DIM == 2 ? j + g.g0 : j, kg = L::DIM == 3 ? k + g.g0 : 0;
+#pragma unroll
+    for (int m = 0; m < NB; m++) {
+      int col;  // Lattice::id2color - 1 (src/lattice.cpp:234-283)
+      if (LAT == SPK_SQ_4N) col = (i + jg) & 1;
+      else if (LAT == SPK_SQ_8N) col = 2 * (jg & 1) + (i & 1);
+      else if (LAT == SPK_TRI) col = 2 * (i & 1) + m;
+      else if (LAT == SPK_SC_6N) col = (i + jg + kg) & 1;
+      else col = 4 * (kg & 1) + 2 * (jg & 1) + (i & 1);
+      if (col == c0) mask[k * sz + j * sy + (long long)i * NB + m] = 0;
+    }
+  }
+}
+
 // Order-independent 64-bit digest of the owned sites: sum over sites of mix64(global index, spin)
 // (splitmix64 finaliser).  Slabs add up to the digest of the whole lattice, so it compares
 // runs of any decomposition and any kernel family at sizes no host copy is wanted for.

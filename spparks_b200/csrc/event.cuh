@@ -347,10 +347,14 @@ __device__ __forceinline__ int site_event_nb26(const EventParams &p, int old, co
 // Returns the new spin (== old when rejected or no event).
 // P16: every spin of the lattice is <= PK16_MAX_SPIN, compares run on packed pairs (see above).
 // kstat (optional): accumulates nevent of the candidate-list apps (host-side variant choice).
+// einitial (optional, `sweep ... mask yes`): receives the initial energy when the event ran to its
+// end, -1 when it returned early (pinned site, no candidate, null bin): the reference's mask
+// update sits after those returns (src/app_potts_neighonly.cpp:90, 107-117).
 template <int MODEL, int RNG, int NN, bool P16 = false>
 __device__ __forceinline__ int site_event(const EventParams &p, int old, const int (&v)[NN], Draws<RNG> &d,
-                                          int *kstat = nullptr) {
+                                          int *kstat = nullptr, int *einitial = nullptr) {
   const int Q = p.nspins;
+  if (einitial) *einitial = -1;
   if (MODEL == SPK_POTTS_PIN && old > Q) return old;  // pinned: no draw (src/app_potts_pin.cpp:97)
 
   constexpr bool PK = P16 && !ising_like(MODEL);
@@ -414,6 +418,7 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
     }
   }
 
+  if (einitial) *einitial = e0;
   // e0 == NN (every neighbour unlike): efinal <= einitial whatever the trial, so the event is
   // accepted without counting; a warp whose lanes all sit in that case (fresh random lattices)
   // skips the second energy altogether

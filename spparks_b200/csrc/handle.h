@@ -34,6 +34,7 @@ struct spk_cuda_handle {
   bool use_fused = true;           // SPK_CUDA_NO_FUSED=1 keeps the per-colour kernels (A/B tests)
   int32_t *base = nullptr;         // allocation incl. ghost planes
   int32_t *spin = nullptr;         // first owned site
+  unsigned char *mask_base = nullptr, *mask = nullptr;  // `sweep ... mask yes`: allocation incl. ghost layers, first owned site
   double *u1 = nullptr, *u2 = nullptr;
   int32_t *seeds = nullptr;
   unsigned long long *naccept = nullptr, *escratch = nullptr;

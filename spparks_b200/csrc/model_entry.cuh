@@ -189,13 +189,13 @@ template <int LAT, int MODEL>
 int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
   SweepArgs a;
   a.spin = h->spin; a.g = h->g; a.c0 = color - 1; a.nloop = nloop; a.ev = h->ev;
-  a.u1 = h->u1; a.u2 = h->u2; a.seeds = h->seeds; a.naccept = h->naccept; a.kstat = h->kstat;
+  a.u1 = h->u1; a.u2 = h->u2; a.seeds = h->seeds; a.naccept = h->naccept; a.kstat = h->kstat; a.mask = h->mask;
   a.mirror_lo = h->mirror_active ? h->mirror_lo : nullptr;
   a.mirror_hi = h->mirror_active ? h->mirror_hi : nullptr;
   if (!local_box(h, box, a.b)) return 0;
   h->nattempt += class_count<LAT>(h, a.b, a.c0) * nloop;
   if (rng == RNG_PHILOX) {
-    if (h->tiled) {
+    if (h->tiled && !h->mask) {  // masked sweeps: generic kernel only
       int rc = h->use_stream ? launch_stream<LAT, MODEL>(h, a) : -1;
       if (rc == 0) return 0;
       if (rc > 0) return fail("stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -214,7 +214,7 @@ int sweep_set_lm(spk_cuda_handle *h, int rng, int color, const int32_t *box, int
 template <int MODEL> int sweep_pair_m(spk_cuda_handle *h, int color, const int32_t *box) {
   SweepArgs a;
   a.spin = h->spin; a.g = h->g; a.c0 = color - 1; a.nloop = 1; a.ev = h->ev;
-  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept; a.kstat = nullptr;
+  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept; a.kstat = nullptr; a.mask = nullptr;
   a.mirror_lo = h->mirror_active ? h->mirror_lo : nullptr;
   a.mirror_hi = h->mirror_active ? h->mirror_hi : nullptr;
   if (!local_box(h, box, a.b)) return 0;

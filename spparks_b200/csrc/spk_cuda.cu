@@ -276,7 +276,7 @@ int fused_sweep(spk_cuda_handle *h, int part) {
   if (!h->tiled || !h->use_fused || h->dim != 2 || !h->fused2d_ok) return -1;
   SweepArgs a;
   a.spin = h->spin; a.g = h->g; a.c0 = 0; a.nloop = 1; a.ev = h->ev;
-  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept; a.kstat = nullptr;
+  a.u1 = nullptr; a.u2 = nullptr; a.seeds = nullptr; a.naccept = h->naccept; a.kstat = nullptr; a.mask = nullptr;
   a.mirror_lo = a.mirror_hi = nullptr;
   a.b = Box{0, h->g.X, 0, h->g.Y, 0, 1};
   if (h->d.nranks == 1 && refresh_ghosts_local(h)) return 1;
@@ -484,6 +484,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   if (h->ev_kstat) cudaEventDestroy(h->ev_kstat);
   cudaFree(h->cl_label); cudaFree(h->cl_size); cudaFree(h->cl_blocksum); cudaFree(h->cl_count);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  cudaFree(h->mask_base);
   cudaFree(h->base); cudaFree(h->base_alt); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
   for (cudaEvent_t e : h->laps) cudaEventDestroy(e);
   if (h->t0) cudaEventDestroy(h->t0);
@@ -787,6 +788,21 @@ int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
   if (!h) return fail("null handle");
   if (nsweeps < 0) return fail("nsweeps must be >= 0");
   CU(cudaSetDevice(h->d.device));
+  if (h->mask) {
+    // `sweep color mask yes` without sectors: the loop sets are the colour sets, all of whose sites
+    // are border sites, so boundary_clear_mask (src/app_lattice.cpp:655) unmasks the whole set
+    // before it is swept: same spins as without masks, mask bytes as the reference leaves them
+    for (int s = 0; s < nsweeps; s++) {
+      h->ev.sweep = first_sweep + (uint32_t)s;
+      for (int color = 1; color <= h->nc; color++) {
+        int rc = spk_cuda_halo_exchange(h);
+        if (!rc) rc = spk_cuda_mask_clear_border(h, nullptr, color);
+        if (!rc) rc = sweep_set(h, RNG_PHILOX, color, nullptr, 1);
+        if (rc) return rc;
+      }
+    }
+    return 0;
+  }
   if (h->d.nranks > 1 && h->comm && h->p2p && nsweeps > 0 && h->tiled) {
     if (h->dim == 3 && h->use_stream) return sweeps_p2p(h, first_sweep, nsweeps);
     if (h->dim == 2 && h->use_fused && h->fused2d_ok && !getenv("SPK_CUDA_OVERLAP_2D"))
@@ -844,6 +860,74 @@ int spk_cuda_reset_counters(spk_cuda_handle *h) {
   CU(cudaMemsetAsync(h->naccept, 0, sizeof(unsigned long long), h->stream));
   h->nattempt_base += h->nattempt;
   h->nattempt = 0;
+  return 0;
+}
+
+int spk_cuda_host_register(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail("null argument");
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail("cudaHostRegister of %zu bytes: %s", bytes, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int spk_cuda_host_unregister(void *ptr) {
+  if (!ptr) return 0;
+  cudaHostUnregister(ptr);
+  cudaGetLastError();
+  return 0;
+}
+
+int spk_cuda_mask_enable(spk_cuda_handle *h, int on) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->d.device));
+  if (!on) {
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->mask_base);
+    h->mask_base = h->mask = nullptr;
+    return 0;
+  }
+  const size_t n = (size_t)(h->nlocal + 2 * (int64_t)h->gh * h->plane);
+  if (!h->mask_base) CU(cudaMalloc(&h->mask_base, n));
+  CU(cudaMemsetAsync(h->mask_base, 0, n, h->stream));  // AppLattice::init: mask[i] = 0 (src/app_lattice.cpp:264-267)
+  h->mask = h->mask_base + (int64_t)h->gh * h->plane;
+  return 0;
+}
+
+int spk_cuda_mask_clear_border(spk_cuda_handle *h, const int32_t *box, int color) {
+  if (!h) return fail("null handle");
+  if (!h->mask) return fail("masking is not enabled (spk_cuda_mask_enable)");
+  if (color < 0 || color > h->nc) return fail("colour %d out of range 0..%d", color, h->nc);
+  CU(cudaSetDevice(h->d.device));
+  Box b;
+  if (!local_box(h, box, b)) return 0;
+  const long long ncell = (long long)(b.ihi - b.ilo) * (b.jhi - b.jlo) * (b.khi - b.klo);
+  const int grid = (int)std::min<long long>(148 * 8, (ncell + 255) / 256);
+  const int multi = h->d.nranks > 1;
+#define SPK_MASK_CASE(LATV)                                                                              \
+  case LATV:                                                                                             \
+    if (color) mask_color_clear_kernel<LATV><<<grid, 256, 0, h->stream>>>(h->mask, h->g, b, color - 1);  \
+    else mask_border_kernel<LATV><<<grid, 256, 0, h->stream>>>(h->mask, h->g, b, multi);                 \
+    break;
+  switch (h->d.lattice) {
+    SPK_MASK_CASE(SPK_SQ_4N) SPK_MASK_CASE(SPK_SQ_8N) SPK_MASK_CASE(SPK_TRI) SPK_MASK_CASE(SPK_SC_6N) SPK_MASK_CASE(SPK_SC_26N)
+    default: return fail("unknown lattice %d", h->d.lattice);
+  }
+#undef SPK_MASK_CASE
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int spk_cuda_download_mask(spk_cuda_handle *h, unsigned char *host, int64_t n) {
+  if (!h || !host) return fail("null argument");
+  if (!h->mask) return fail("masking is not enabled (spk_cuda_mask_enable)");
+  if (n != h->nlocal) return fail("download of %lld mask bytes, slab owns %lld sites", (long long)n, (long long)h->nlocal);
+  CU(cudaSetDevice(h->d.device));
+  CU(cudaMemcpyAsync(host, h->mask, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

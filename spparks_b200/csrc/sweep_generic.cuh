@@ -17,6 +17,7 @@ struct SweepArgs {
   const double *u1, *u2;  // RNG_INJECTED: per owned site
   int32_t *seeds;         // RNG_STRICT: per owned site
   unsigned long long *naccept;
+  unsigned char *mask;    // `sweep ... mask yes`: one byte per site, indexed like spin (null = off)
   unsigned long long *kstat;  // candidate-list apps: sum of nevent over the sites (streaming kernel; null = off)
   // peer-memory halo (streaming kernel, multi-GPU slabs): updates of local plane 0 / Z-1 are also
   // stored into the ring neighbour's ghost plane over NVLink (null = no mirror)
@@ -102,6 +103,27 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const __grid_constan
 
     int cur = a.spin[self];
     const int before = cur;
+    // `sweep ... mask yes` (src/app_lattice.cpp:784-792, 809-819): a masked site is skipped; after an
+    // event that ran to its end the site is masked if einitial < numneigh/2, and a change unmasks
+    // every neighbour (src/app_potts.cpp:140-145).  Same-colour sites are not neighbours, so the
+    // mask bytes a launch reads are not the ones it writes.
+    bool masked = a.mask != nullptr && a.mask[self] != 0;
+    auto mask_after = [&](int einit, bool changed) {
+      if (a.mask == nullptr || einit < 0) return;
+      if (2 * einit < NN) { a.mask[self] = 1; masked = true; }
+      if (changed) {
+        auto clear = [&](auto mm) {
+#pragma unroll
+          for (int n = 0; n < NN; n++) {
+            constexpr int M = decltype(mm)::value;
+            const Off o = L::off(M, n);
+            a.mask[zk[o.dz + 1] * sz + yj[o.dy + 1] * sy + (long long)xi[o.dx + 1] * NB + o.m] = 0;
+          }
+        };
+        if (LAT == SPK_TRI && m == 1) clear(std::integral_constant<int, 1>{});
+        else clear(std::integral_constant<int, 0>{});
+      }
+    };
     // global site index keys the random stream, so any slab decomposition gives the same run
     long long jg = j, kg = k;
     if constexpr (L::DIM == 2) jg += g.g0; else kg += g.g0;
@@ -111,9 +133,11 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const __grid_constan
     if constexpr (RNG == RNG_STRICT) {
       Draws<RNG_STRICT> d;
       d.seed = a.seeds[lsite];
-      for (int l = 0; l < a.nloop; l++) {
-        int nw = site_event<MODEL, RNG, NN>(a.ev, cur, v, d);
+      for (int l = 0; l < a.nloop && !masked; l++) {
+        int einit;
+        int nw = site_event<MODEL, RNG, NN>(a.ev, cur, v, d, nullptr, &einit);
         accepted += (nw != cur);
+        mask_after(einit, nw != cur);
         cur = nw;
       }
       a.seeds[lsite] = d.seed;
@@ -121,19 +145,25 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const __grid_constan
       Draws<RNG_INJECTED> d;
       d.u1 = a.u1[lsite];
       d.u2 = a.u2[lsite];
-      int nw = site_event<MODEL, RNG, NN>(a.ev, cur, v, d);
-      accepted += (nw != cur);
-      cur = nw;
+      if (!masked) {
+        int einit;
+        int nw = site_event<MODEL, RNG, NN>(a.ev, cur, v, d, nullptr, &einit);
+        accepted += (nw != cur);
+        mask_after(einit, nw != cur);
+        cur = nw;
+      }
     } else {
       // block shared with the other class sites of the strip (event.cuh: philox_words)
       const unsigned long long leader = gsite - (unsigned long long)(philox_leader_shift<MODEL>(i) * NB);
-      for (int l = 0; l < a.nloop; l++) {
+      for (int l = 0; l < a.nloop && !masked; l++) {
         const uint4 blk = philox4x32_10((uint32_t)leader, (uint32_t)(leader >> 32), a.ev.sweep,
                                         (uint32_t)l * 16u + (uint32_t)(a.c0 + 1), a.ev.k0, a.ev.k1);
         Draws<RNG_PHILOX> d;
         philox_words<MODEL>(blk, i, d.w1, d.w2);
-        int nw = site_event<MODEL, RNG, NN>(a.ev, cur, v, d);
+        int einit;
+        int nw = site_event<MODEL, RNG, NN>(a.ev, cur, v, d, nullptr, &einit);
         accepted += (nw != cur);
+        mask_after(einit, nw != cur);
         cur = nw;
       }
     }

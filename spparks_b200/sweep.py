@@ -150,6 +150,17 @@ class LatticeSweep:
         """0 = single GPU, 1 = NCCL exchange per colour step, 2 = peer-memory stores (no exchange)."""
         return int(self.L.spk_cuda_halo_mode(self.h))
 
+    def mask_enable(self, on=True):
+        _lib.check(self.L.spk_cuda_mask_enable(self.h, 1 if on else 0))
+
+    def mask_clear_border(self, box=None, color=0):
+        _lib.check(self.L.spk_cuda_mask_clear_border(self.h, _box(box), color))
+
+    def download_mask(self):
+        out = np.empty(self.nlocal, dtype=np.uint8)
+        _lib.check(self.L.spk_cuda_download_mask(self.h, out.ctypes.data_as(C.c_void_p), self.nlocal))
+        return out
+
     def digest(self):
         """Order-independent 64-bit digest of the owned spins (global site index, value)."""
         d = C.c_uint64()

@@ -129,6 +129,41 @@ def gen_sets(model, q, lattice, n, T, rng):
                         n=np.array(n, dtype=np.int32), q=q, T=T, spins0=spins0, k=k, after=after)
 
 
+def gen_masksets(model, q, lattice, n, T, npass, sector, rng, blocky=True):
+    """`sweep color mask yes` + sectors: npass passes over the sets in iterate_rejection order with the
+    reference's boundary_clear_mask / mask rule, injected uniforms; spins and mask bytes after every pass."""
+    ns = nsites(lattice, n)
+    with tempfile.TemporaryDirectory() as tmp:
+        spins0 = random_spins(rng, model, q, ns, 0.05 if model == "potts/pin" else 0.0, blocky)
+        spins0.tofile(os.path.join(tmp, "s0.bin"))
+        ks = rng.integers(1, IM - 1, size=(npass, ns), dtype=np.int32)
+        lines = header(model, q, lattice, n) + ["sweep color mask yes", "sector %s" % sector, "temperature %r" % T,
+                                                "run 0.0", "@load s0.bin"]
+        for p in range(npass):
+            ks[p].tofile(os.path.join(tmp, "k%d.bin" % p))
+            lines += ["@masksweep k%d.bin m%d.bin" % (p, p), "@save s%d.bin" % (p + 1)]
+        run_driver(lines, tmp)
+        after = np.stack([ints(tmp, "s%d.bin" % (p + 1)) for p in range(npass)])
+        masks = np.stack([ints(tmp, "m%d.bin" % p) for p in range(npass)]).astype(np.uint8)
+    nsec = {"yes": 4 if DIM[lattice] == 2 else 8}.get(sector, None) or int(sector)
+    name = "masksets_%s_%s_s%d.npz" % (tag(model), tag(lattice), nsec)
+    np.savez_compressed(os.path.join(HERE, name), n=np.array(n, dtype=np.int32), q=q, T=T, nsector=nsec,
+                        spins0=spins0, k=ks, after=after, mask=masks)
+
+
+def main_mask():
+    """SURVEY §8f rank 3 tail: `sweep ... mask yes`:  python tests/golden/make_golden.py mask"""
+    rng = np.random.default_rng(20261019)
+    gen_masksets("potts", 4, "sc/26n", (8, 8, 8), 0.0, 4, "yes", rng)
+    gen_masksets("potts/neighonly", 5, "sc/26n", (8, 6, 8), 0.0, 4, "yes", rng)
+    gen_masksets("potts/pin", 4, "sc/26n", (8, 8, 6), 0.0, 3, "2", rng)
+    gen_masksets("ising", 2, "sq/4n", (16, 12, 1), 0.0, 4, "yes", rng)
+    gen_masksets("ising", 2, "sq/4n", (12, 12, 1), 0.8, 3, "2", rng, blocky=False)
+    gen_masksets("potts", 6, "tri", (8, 10, 1), 0.0, 4, "yes", rng, blocky=False)
+    gen_masksets("potts/neigh", 3, "sq/8n", (12, 10, 1), 0.0, 3, "yes", rng)
+    gen_masksets("ising/single", 2, "sc/6n", (8, 6, 6), 0.0, 3, "4", rng)
+
+
 def gen_strict(model, q, lattice, n, T, nsweeps, rng):
     ns = nsites(lattice, n)
     dt = DT_SWEEP[model](q, MAXNEIGH[lattice])
@@ -202,5 +237,7 @@ def main_variants():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         main_variants()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mask":
+        main_mask()
     else:
         main()

@@ -55,6 +55,67 @@ def test_sector_color_sets_bit_exact_vs_reference(path):
     assert s.counters()[1] == s.nlocal
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "masksets_*.npz"))), ids=os.path.basename)
+def test_masked_sector_passes_bit_exact_vs_reference(path):
+    """`sweep color mask yes` with sectors: spins and mask bytes after every pass over the sets
+    against the UNMODIFIED reference (its own boundary_clear_mask, mask rule and events)."""
+    g = np.load(path)
+    model, lat = split_name(path, "masksets")
+    nx, ny, nz = [int(v) for v in g["n"]]
+    s = _sweep(model, lat, g["n"], g["q"], g["T"])
+    o = O.Oracle(model, lat, nx, ny, nz, int(g["q"]), float(g["T"]))
+    nsector = int(g["nsector"])
+    s.upload(g["spins0"])
+    s.mask_enable()
+    nattempt = 0
+    for p in range(g["k"].shape[0]):
+        u1, u2 = O.injected_uniforms(g["k"][p])
+        for sec in range(nsector):
+            box = o.sector_box(nsector, sec + 1)
+            s.mask_clear_border(box)
+            for c in range(s.ncolors):
+                s.sweep_color_injected(c + 1, u1, u2, box=box)
+        assert np.array_equal(s.download(), g["after"][p]), "spins after pass %d" % p
+        assert np.array_equal(s.download_mask(), g["mask"][p]), "mask after pass %d" % p
+
+
+@pytest.mark.parametrize("model,lat,n,q,nsector", [
+    ("potts", "sc/26n", (24, 16, 12), 5, 8), ("potts/neighonly", "sc/26n", (16, 12, 10), 4, 2),
+    ("ising", "sq/4n", (64, 40, 1), 2, 4), ("potts", "tri", (24, 18, 1), 4, 4), ("potts/pin", "sc/6n", (12, 10, 8), 3, 1),
+], ids=lambda v: str(v).replace(" ", ""))
+def test_masked_philox_sweeps_vs_oracle(model, lat, n, q, nsector):
+    """Production (Philox) mode with masks at T = 0, sectors x colours and (nsector = 1) plain colour
+    sets through spk_cuda_sweeps: spins, masks and counters against the oracle."""
+    rng = np.random.default_rng(13)
+    o = O.Oracle(model, lat, n[0], n[1], n[2], q, 0.0)
+    spins = np.repeat(rng.integers(1, (2 if model == "ising" else q) + 1, size=(o.nsites + 7) // 8, dtype=np.int32), 8)[:o.nsites].copy()
+    if model == "potts/pin":
+        spins[rng.random(o.nsites) < 0.05] = q + 1
+    s = _sweep(model, lat, n, q, 0.0, seed=4711)
+    s.upload(spins)
+    s.mask_enable()
+    want, mask = spins.copy(), np.zeros(o.nsites, dtype=np.uint8)
+    nacc = 0
+    colors = o.colors()
+    for sw in range(4):
+        if nsector == 1:
+            for c in range(1, o.ncolors + 1):
+                mask[colors == c] = 0  # a colour set as loop set: all of it is border (boundary_clear_mask)
+                nacc += o.halfsweep_philox_mask(want, mask, 4711, sw, c)
+            s.sweeps(sw, 1)
+        else:
+            for sec in range(nsector):
+                box = o.sector_box(nsector, sec + 1)
+                o.boundary_clear_mask(mask, box)
+                s.mask_clear_border(box)
+                for c in range(1, o.ncolors + 1):
+                    nacc += o.halfsweep_philox_mask(want, mask, 4711, sw, c, box=box)
+                    s.sweep_color(sw, c, box=box)
+        assert np.array_equal(s.download(), want), sw
+        assert np.array_equal(s.download_mask(), mask), sw
+    assert s.counters() == (nacc, 4 * o.nsites)
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "strict_*.npz"))), ids=os.path.basename)
 def test_strict_runs_bit_exact_vs_reference(path):
     """`sweep color/strict`: whole multi-sweep runs of the reference, spin for spin."""

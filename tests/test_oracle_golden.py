@@ -90,6 +90,29 @@ def test_sector_color_pass_matches_reference(path):
     assert np.array_equal(spin, g["after"])
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "masksets_*.npz"))), ids=os.path.basename)
+def test_masked_sector_passes_match_reference(path):
+    """`sweep color mask yes` with sectors (src/app_lattice.cpp:655, 784-792, 1158-1164 and the mask
+    updates inside the events): spins AND mask bytes after every pass over the sets."""
+    g = np.load(path)
+    model, lat = split_name(path, "masksets")
+    nx, ny, nz = [int(v) for v in g["n"]]
+    o = O.Oracle(model, lat, nx, ny, nz, int(g["q"]), float(g["T"]))
+    nsector = int(g["nsector"])
+    spins = g["spins0"].copy()
+    mask = np.zeros(o.nsites, dtype=np.uint8)
+    for p in range(g["k"].shape[0]):
+        u1, u2 = O.injected_uniforms(g["k"][p])
+        for sec in range(nsector):
+            box = o.sector_box(nsector, sec + 1)
+            o.boundary_clear_mask(mask, box)
+            for c in range(o.ncolors):
+                o.halfsweep_injected_mask(spins, mask, c + 1, u1, u2, box=box)
+        assert np.array_equal(spins, g["after"][p]), "spins after pass %d" % p
+        assert np.array_equal(mask, g["mask"][p]), "mask after pass %d" % p
+    assert g["mask"].any() and not g["mask"].all()  # the fixture exercises both skipped and live sites
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "strict_*.npz"))), ids=os.path.basename)
 def test_strict_runs_match_reference(path):
     """`sweep color/strict` full runs: spins, per-site seeds, Naccept and energy."""

@@ -205,3 +205,78 @@ run %.17g
         host, dev = r[4:8], r[8:12]   # Energy Nclust <N> <R> | the same four from the device
         assert host == dev, r
     assert int(rows[-1][5]) < int(rows[0][5])  # the lattice coarsens
+
+
+@pytest.mark.parametrize("case", [STRICT_CASES[0], STRICT_CASES[1], STRICT_CASES[3]], ids=lambda c: c["app"] + "-" + c["lat"])
+def test_mask_yes_script_identical_to_reference(case):
+    """`sweep color/strict mask yes`: the plugin keeps the mask bytes on the device
+    (spk_cuda_mask_enable / _clear_border); the reference forbids sectors with color/strict, so the
+    loop sets are the colour sets, whose masks boundary_clear_mask clears before every pass — the
+    table must equal the reference's own `mask yes` run (and its `mask no` run)."""
+    def script(style, mask):
+        app = style if case["app"].startswith("ising") else "%s %d" % (style, case["q"])
+        return STRICT.format(**dict(case, app=app)).replace("sweep color/strict", "sweep color/strict mask " + mask)
+    ref = stats_rows(run(SPK_REF, script(case["app"], "yes")))
+    assert ref == stats_rows(run(SPK_REF, script(case["app"], "no")))
+    gpu = stats_rows(run(SPK_CUDA, script(case["app"] + "/cuda", "yes")))
+    assert len(ref) >= 4 and gpu == ref
+
+
+def test_mask_yes_with_sectors_relaxes_like_mask_no():
+    """`sweep color mask yes` + `sector yes` at T = 0 through the plugin (the masked path that the
+    reference fixtures pin at the ABI level): same attempts and time axis as `mask no`, energies
+    relax to the same level (masking must not change the answer in a statistical sense, doc/sweep.txt)."""
+    def script(mask):
+        return """seed 99
+app_style potts/cuda 20
+dimension 3
+lattice sc/26n 1.0
+region box block 0 24 0 24 0 24
+create_box box
+create_sites box
+set site range 1 20
+cuda_seed 5
+sweep color mask %s
+sector yes
+temperature 0.0
+diag_style energy
+stats 0.25
+run 1.0
+""" % mask
+    yes, no = stats_rows(run(SPK_CUDA, script("yes"))), stats_rows(run(SPK_CUDA, script("no")))
+    assert [r[3] for r in yes] == [r[3] for r in no] and len(yes) == 5
+    assert int(yes[-1][1]) + int(yes[-1][2]) == int(no[-1][1]) + int(no[-1][2]) == 20 * 24 ** 3
+    e_yes, e_no = float(yes[-1][4]), float(no[-1][4])
+    assert e_yes < 0.8 * float(yes[0][4]) and abs(e_yes - e_no) < 0.03 * e_no, (e_yes, e_no)
+
+
+def test_finish_line_and_host_sync_option():
+    """The plugin prints its sweep-loop throughput next to the reference's timing breakdown, and
+    `cuda_host_sync no` (only /cuda diagnostics read the lattice during the run) leaves the table
+    unchanged while the host copy is refreshed only when the run ends."""
+    base = """seed 3
+app_style ising/cuda
+dimension 2
+lattice sq/4n 1.0
+region box block 0 128 0 96 -0.5 0.5
+create_box box
+create_sites box
+set site range 1 2
+cuda_seed 17
+%s
+sweep color
+sector no
+temperature 1.0
+diag_style energy/cuda
+stats 2.0
+run 10.0
+diag_style energy
+run 0.0
+"""
+    a = run(SPK_CUDA, base % "cuda_host_sync yes")
+    b = run(SPK_CUDA, base % "cuda_host_sync no")
+    ra, rb = stats_rows(a), stats_rows(b)
+    assert ra == rb and len(ra) >= 7
+    # the final `run 0.0` adds the host-side energy of the downloaded lattice: equal to the device's
+    assert ra[-1][4] == ra[-1][5]
+    assert re.search(r"CUDA sweep loop: .* Gsites/s", a)
