@@ -16,7 +16,11 @@ def test_reference_arm_prints_the_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "site_updates_per_sec" and line["unit"] == "Gsites/s"
     assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
-    assert line["config"]["workload"] == "ising_sq4n_16384"
+    assert line["config"]["workload"] == "potts_neighonly_sc26n_1024"  # BASELINE configs[2], the headline
+    # the arm states what it really ran: a bounded sample, the reference's own random stream
+    rs = line["reference_sample"]
+    assert rs["per_replica_cells"] == [96, 96, 96] and rs["scaled_from_per_gpu_cells"] == [1024, 1024, 1024]
+    assert rs["replicas"] == line["cpu_baseline"]["cores"] and "rng" in rs
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "Gsites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
