@@ -44,7 +44,7 @@ enum { SPK_SQ_4N = 2, SPK_SQ_8N = 3, SPK_TRI = 4, SPK_SC_6N = 5, SPK_SC_26N = 6 
 typedef struct {
   int32_t model;        /* SPK_ISING ... */
   int32_t lattice;      /* SPK_SQ_4N ... */
-  int32_t nx, ny, nz;   /* GLOBAL extents in unit cells, all even (src/lattice.cpp:187-228); nz = 1 in 2-D */
+  int32_t nx, ny, nz;   /* GLOBAL extents in unit cells, even (tri: only nx must be; src/lattice.cpp:187-228); nz = 1 in 2-D */
   int32_t nspins;       /* Q of `app_style potts Q`; ignored for ising */
   double temperature;   /* `temperature` command (src/app_lattice.cpp:889-894) */
   uint64_t seed;        /* key of the counter-based Philox stream (replaces ranapp, src/app_lattice.cpp:274-278) */
@@ -75,6 +75,15 @@ int spk_cuda_download_spins(spk_cuda_handle *h, int32_t *host, int64_t n);
 /* `temperature` (src/app_lattice.cpp:889-894): rebuilds the exp() acceptance tables on the host */
 int spk_cuda_set_temperature(spk_cuda_handle *h, double temperature);
 
+/* `set site range lo hi` ON THE DEVICE, bit for bit the reference's values (src/set.cpp:582-627,
+ * default loop all / no region, fraction or condition): the one Park-Miller stream that Set walks
+ * over the global site ids is evaluated per site with a modular power.  park_seed is the state
+ * of `new RandomPark(ranmaster->uniform())` (src/set.cpp:598: (int)(u*(2^31-1)), 0 -> 1). */
+int spk_cuda_set_site_range(spk_cuda_handle *h, int32_t park_seed, int32_t lo, int32_t hi);
+/* site_energy(i) (src/app_potts.cpp:97-104) of every owned site, one byte each, for
+ * `dump ... energy` (DumpText::pack_energy, src/dump_text.cpp:670) without the host's 2*maxneigh
+ * gathers per site */
+int spk_cuda_site_energy(spk_cuda_handle *h, unsigned char *host, int64_t n);
 /* device-side synthetic initialisation for lattices too large for the host path
  * (distribution of `set site range lo hi`, src/set.cpp:582-627, and of `pin f 0 0`,
  * src/app_potts_pin.cpp:262-283; NOT the reference's random stream) */

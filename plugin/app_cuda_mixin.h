@@ -87,6 +87,29 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       if (narg != 1) this->error->all(FLERR,"Illegal cuda_seed command");
       seed = strtoull(arg[0],NULL,10);
       seed_set = 1;
+    } else if (strcmp(command,"cuda_set") == 0) {
+      // cuda_set site range lo hi  ==  set site range lo hi (src/set.cpp:582-627, loop all,
+      // no region/fraction/if), computed on the device: same master-stream draw, same values
+      if (narg != 4 || strcmp(arg[0],"site") != 0 || strcmp(arg[1],"range") != 0)
+        this->error->all(FLERR,"Illegal cuda_set command (cuda_set site range lo hi)");
+      if (this->sites_exist == 0) this->error->all(FLERR,"Set command before sites exist");
+      int lo = atoi(arg[2]), hi = atoi(arg[3]);
+      int pseed = static_cast<int> (this->ranmaster->uniform()*2147483647);   // new RandomPark(double)
+      if (pseed == 0) pseed = 1;
+      spk_cuda_handle *tmp = NULL;
+      spk_cuda_desc desc;
+      fill_desc(desc,0.0);
+      check(spk_cuda_create(&desc,&tmp));
+      int rc = spk_cuda_set_site_range(tmp,pseed,lo,hi);
+      if (!rc) rc = spk_cuda_download_spins(tmp,this->iarray[0],this->nlocal);
+      spk_cuda_destroy(tmp);
+      check(rc);
+      bigint nbig = this->nlocal, allcount;
+      MPI_Allreduce(&nbig,&allcount,1,MPI_SPK_BIGINT,MPI_SUM,this->world);
+      if (this->me == 0) {
+        if (this->screen) fprintf(this->screen,"  " BIGINT_FORMAT " settings made for site\n",allcount);
+        if (this->logfile) fprintf(this->logfile,"  " BIGINT_FORMAT " settings made for site\n",allcount);
+      }
     } else if (strcmp(command,"cuda_host_sync") == 0) {
       // yes (default): iarray[0] is refreshed before every Output::compute, as host-side
       //   diagnostics and dumps expect
@@ -114,32 +137,6 @@ class AppCudaMixin : public Base, public SpkCudaHost {
   {
     Base::init_app();   // spin validity check, dt_sweep of potts/neighonly
 
-    // the device kernels address sites by lattice index: need a `create_sites box` lattice
-    // that is fully periodic (domain->nx,ny,nz set, src/create_sites.cpp:248-252) and
-    // one of the five supported styles (enum of src/lattice.cpp:32-33)
-
-    Domain *domain = this->domain;
-    if (domain->lattice == NULL || domain->nx == 0)
-      this->error->all(FLERR,"app_style */cuda requires create_sites box on a periodic lattice");
-    int lat = domain->lattice->style;
-    if (spk_cuda_maxneigh(lat) == 0 || this->maxneigh != spk_cuda_maxneigh(lat))
-      this->error->all(FLERR,"app_style */cuda does not support this lattice style");
-
-    // one process <-> one GPU; with several ranks every rank must own one slab of the
-    // last dimension (processors 1 1 P in 3d, 1 P 1 in 2d)
-
-    int sd = domain->dimension - 1;
-    for (int d = 0; d < 3; d++)
-      if (d != sd && domain->procgrid[d] != 1)
-        this->error->all(FLERR,"app_style */cuda needs a slab decomposition (processors 1 1 P)");
-    if (this->nprocs > 1 && domain->myloc[sd] != this->me)
-      this->error->all(FLERR,"app_style */cuda needs slab index == MPI rank");
-
-    tagint first = this->nlocal ? this->id[0] : 1;
-    for (int i = 0; i < this->nlocal; i++)
-      if (this->id[i] != first+i)
-        this->error->all(FLERR,"app_style */cuda requires sites ordered by ID");
-
     if (!seed_set) {
       // like ranapp (src/app_lattice.cpp:274-278): derived from the `seed` command, once
       seed = (uint64_t) (this->ranmaster->uniform() * 9007199254740992.0);
@@ -149,21 +146,13 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     if (handle) { spk_cuda_destroy(handle); handle = NULL; }
 
     spk_cuda_desc desc;
-    desc.model = MODEL;
-    desc.lattice = lat;
-    desc.nx = domain->nx; desc.ny = domain->ny; desc.nz = domain->nz;
-    desc.nspins = nspins_cuda;
-    desc.temperature = this->temperature;
-    desc.seed = seed;
-    desc.device = device;
-    desc.rank = this->me;
-    desc.nranks = this->nprocs;
+    fill_desc(desc,this->temperature);
     check(spk_cuda_create(&desc,&handle));
     if (this->Lmask) check(spk_cuda_mask_enable(handle,1));   // src/app_lattice.cpp:258-267
 
     // tri with an odd number of rows: the two basis sites of the middle row fall into different
     // sectors (y = (j+1/2)*sqrt(3) vs ymid, src/app_lattice.cpp:959-974): not a box of cells
-    if (lat == SPK_TRI && this->nsector >= 4 && (slab_hi()-slab_lo()) % 2)
+    if (desc.lattice == SPK_TRI && this->nsector >= 4 && (slab_hi()-slab_lo()) % 2)
       this->error->all(FLERR,"app_style */cuda: sectors in y need an even number of tri rows per processor");
 
     // page-lock the host spins once: uploads / downloads then run at full PCIe speed
@@ -312,6 +301,47 @@ class AppCudaMixin : public Base, public SpkCudaHost {
   void *pinned;
   size_t pinned_bytes;
   double perf_sites,perf_seconds;
+
+  // geometry checks + descriptor of this rank's slab (init_app, cuda_set)
+
+  void fill_desc(spk_cuda_desc &desc, double temperature)
+  {
+    // the device kernels address sites by lattice index: need a `create_sites box` lattice
+    // that is fully periodic (domain->nx,ny,nz set, src/create_sites.cpp:248-252) and
+    // one of the five supported styles (enum of src/lattice.cpp:32-33)
+
+    Domain *domain = this->domain;
+    if (domain->lattice == NULL || domain->nx == 0)
+      this->error->all(FLERR,"app_style */cuda requires create_sites box on a periodic lattice");
+    int lat = domain->lattice->style;
+    if (spk_cuda_maxneigh(lat) == 0 || this->maxneigh != spk_cuda_maxneigh(lat))
+      this->error->all(FLERR,"app_style */cuda does not support this lattice style");
+
+    // one process <-> one GPU; with several ranks every rank must own one slab of the
+    // last dimension (processors 1 1 P in 3d, 1 P 1 in 2d)
+
+    int sd = domain->dimension - 1;
+    for (int d = 0; d < 3; d++)
+      if (d != sd && domain->procgrid[d] != 1)
+        this->error->all(FLERR,"app_style */cuda needs a slab decomposition (processors 1 1 P)");
+    if (this->nprocs > 1 && domain->myloc[sd] != this->me)
+      this->error->all(FLERR,"app_style */cuda needs slab index == MPI rank");
+
+    tagint first = this->nlocal ? this->id[0] : 1;
+    for (int i = 0; i < this->nlocal; i++)
+      if (this->id[i] != first+i)
+        this->error->all(FLERR,"app_style */cuda requires sites ordered by ID");
+
+    desc.model = MODEL;
+    desc.lattice = lat;
+    desc.nx = domain->nx; desc.ny = domain->ny; desc.nz = domain->nz;
+    desc.nspins = nspins_cuda;
+    desc.temperature = temperature;
+    desc.seed = seed;
+    desc.device = device;
+    desc.rank = this->me;
+    desc.nranks = this->nprocs;
+  }
 
   // this rank's slab of the last dimension in global cells (init_app checked slab index == rank)
   int slab_lo()

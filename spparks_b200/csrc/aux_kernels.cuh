@@ -15,6 +15,45 @@ __global__ void randomize_kernel(int32_t *spin, long long n, long long goff, uns
   }
 }
 
+// `set site range lo hi` of the reference, bit for bit (src/set.cpp:582-627, default `loop all`, no
+// region / fraction / condition): ONE Park-Miller stream (src/random_park.cpp:79-97) is walked over
+// the global ids 1..N, so the site with global index s (0-based) takes draw number s+1:
+//   state = seed0 * 16807^(s+1) mod (2^31-1),  value = lo + min((int)(state*AM*range), range-1).
+// A warp covers 32 consecutive sites per step; each lane jumps to its first state with a modular
+// power and then advances by 32 draws at a time (multiplier 16807^32 mod (2^31-1)).
+__device__ __forceinline__ uint32_t pm_mulmod(uint32_t a, uint32_t b) {  // a*b mod 2^31-1, a,b < 2^31-1
+  const uint64_t p = (uint64_t)a * b;
+  uint32_t r = (uint32_t)(p & 0x7FFFFFFFu) + (uint32_t)(p >> 31);
+  r = (r & 0x7FFFFFFFu) + (r >> 31);
+  return r == 0x7FFFFFFFu ? 0u : r;
+}
+__device__ __forceinline__ uint32_t pm_powmod(uint32_t base, unsigned long long e) {
+  uint32_t r = 1u;
+  while (e) {
+    if (e & 1ull) r = pm_mulmod(r, base);
+    base = pm_mulmod(base, base);
+    e >>= 1;
+  }
+  return r;
+}
+__global__ void __launch_bounds__(256) set_range_kernel(int32_t *spin, long long n, long long goff, uint32_t seed0, int lo,
+                                                        int range) {
+  const uint32_t step32 = pm_powmod(16807u, 32ull);
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long per = ((n + 31) / 32 + nwarps - 1) / nwarps * 32;  // sites per warp, multiple of 32
+  const long long first = warp * per, last = first + per < n ? first + per : n;
+  if (first >= n) return;
+  uint32_t state = pm_mulmod(seed0, pm_powmod(16807u, (unsigned long long)(first + lane + goff) + 1ull));
+  for (long long s = first + lane; s < last; s += 32) {
+    const double u = (1.0 / 2147483647) * (double)(int)state;  // RandomPark::uniform: AM*seed
+    int i = (int)(u * range) + 1;                               // irandom
+    if (i > range) i = range;
+    spin[s] = i - 1 + lo;
+    state = pm_mulmod(state, step32);
+  }
+}
+
 // Bernoulli(fraction) pinning, the large-lattice stand-in for `pin f 0 0`
 // (src/app_potts_pin.cpp:262-283 draws ndesired random sites; here each site is pinned
 // independently with the same probability).  Pinned value = Q+1 (src/app_potts_pin.cpp:271).
@@ -97,6 +136,42 @@ __global__ void __launch_bounds__(256) mask_color_clear_kernel(unsigned char *ma
       else if (LAT == SPK_SC_6N) col = (i + jg + kg) & 1;
       else col = 4 * (kg & 1) + 2 * (jg & 1) + (i & 1);
       if (col == c0) mask[k * sz + j * sy + (long long)i * NB + m] = 0;
+    }
+  }
+}
+
+// site_energy(i) of every owned site (src/app_potts.cpp:97-104), one byte each: what
+// `dump ... energy` (DumpText::pack_energy, src/dump_text.cpp:670) asks the app for site by site
+template <int LAT>
+__global__ void __launch_bounds__(256) site_energy_kernel(const int32_t *__restrict__ spin, Geo g, unsigned char *out) {
+  using L = Lat<LAT>;
+  constexpr int NN = L::NN, NB = L::NB;
+  const long long sy = (long long)g.X * NB, sz = sy * g.Y;
+  const long long ncell = (long long)g.X * g.Y * g.Z;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % g.X);
+    const int j = (int)((c / g.X) % g.Y);
+    const int k = (int)(c / ((long long)g.X * g.Y));
+    const int xi[3] = {i == 0 ? g.X - 1 : i - 1, i, i == g.X - 1 ? 0 : i + 1};
+    int yj[3], zk[3];
+    if (L::DIM == 2) {
+      yj[0] = j == 0 ? g.lo_wrap : j - 1; yj[1] = j; yj[2] = j == g.Y - 1 ? g.hi_wrap : j + 1;
+      zk[0] = zk[1] = zk[2] = 0;
+    } else {
+      yj[0] = j == 0 ? g.Y - 1 : j - 1; yj[1] = j; yj[2] = j == g.Y - 1 ? 0 : j + 1;
+      zk[0] = k == 0 ? g.lo_wrap : k - 1; zk[1] = k; zk[2] = k == g.Z - 1 ? g.hi_wrap : k + 1;
+    }
+#pragma unroll
+    for (int m = 0; m < NB; m++) {
+      const long long self = zk[1] * sz + yj[1] * sy + (long long)i * NB + m;
+      const int me = spin[self];
+      int e = 0;
+#pragma unroll
+      for (int n = 0; n < NN; n++) {
+        const Off o = L::off(m, n);
+        e += (spin[zk[o.dz + 1] * sz + yj[o.dy + 1] * sy + (long long)xi[o.dx + 1] * NB + o.m] != me);
+      }
+      out[self] = (unsigned char)e;
     }
   }
 }

@@ -542,6 +542,10 @@ int spk_cuda_set_temperature(spk_cuda_handle *h, double temperature) {
 int spk_cuda_randomize(spk_cuda_handle *h, uint64_t seed, int32_t lo, int32_t hi) {
   if (!h) return fail("null handle");
   if (hi < lo) return fail("empty value range");
+  {  // the kernels assume spins in 1..Q (Q+1 = pinned, potts/pin), as the reference's init_app enforces
+    const int top = ising_like(h->d.model) ? 2 : h->d.nspins + (h->d.model == SPK_POTTS_PIN ? 1 : 0);
+    if (lo < 1 || hi > top) return fail("One or more sites have invalid values (range %d..%d outside 1..%d)", lo, hi, top);
+  }
   CU(cudaSetDevice(h->d.device));
   const int64_t goff = (int64_t)h->g.g0 * h->plane;
   randomize_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, goff, seed, lo, (uint32_t)(hi - lo + 1));
@@ -549,6 +553,48 @@ int spk_cuda_randomize(spk_cuda_handle *h, uint64_t seed, int32_t lo, int32_t hi
   neigh_mode_reset(h);
   h->launches++;
   CU(cudaGetLastError());
+  return 0;
+}
+
+int spk_cuda_set_site_range(spk_cuda_handle *h, int32_t park_seed, int32_t lo, int32_t hi) {
+  if (!h) return fail("null handle");
+  if (hi < lo) return fail("Illegal set command");
+  if (park_seed < 1 || park_seed >= 2147483647) return fail("Park-Miller seed must lie in [1, 2^31-2]");
+  const int top = ising_like(h->d.model) ? 2 : h->d.nspins + (h->d.model == SPK_POTTS_PIN ? 1 : 0);
+  if (lo < 1 || hi > top) return fail("One or more sites have invalid values (range %d..%d outside 1..%d)", lo, hi, top);
+  CU(cudaSetDevice(h->d.device));
+  const long long goff = (long long)h->g.g0 * h->plane;
+  set_range_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, goff, (uint32_t)park_seed, lo, hi - lo + 1);
+  h->ghosts_valid = false;
+  neigh_mode_reset(h);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int spk_cuda_site_energy(spk_cuda_handle *h, unsigned char *host, int64_t n) {
+  if (!h || !host) return fail("null argument");
+  if (n != h->nlocal) return fail("site energies of %lld sites, slab owns %lld", (long long)n, (long long)h->nlocal);
+  CU(cudaSetDevice(h->d.device));
+  int rc = spk_cuda_halo_exchange(h);  // site_energy reads the ghosts (src/dump.cpp: comm before the pack)
+  if (rc) return rc;
+  unsigned char *d = nullptr;
+  CU(cudaMalloc(&d, (size_t)n));
+  const long long ncell = (long long)h->g.X * h->g.Y * h->g.Z;
+  const int grid = (int)std::min<long long>(148 * 8, (ncell + 255) / 256);
+  switch (h->d.lattice) {
+    case SPK_SQ_4N: site_energy_kernel<SPK_SQ_4N><<<grid, 256, 0, h->stream>>>(h->spin, h->g, d); break;
+    case SPK_SQ_8N: site_energy_kernel<SPK_SQ_8N><<<grid, 256, 0, h->stream>>>(h->spin, h->g, d); break;
+    case SPK_TRI: site_energy_kernel<SPK_TRI><<<grid, 256, 0, h->stream>>>(h->spin, h->g, d); break;
+    case SPK_SC_6N: site_energy_kernel<SPK_SC_6N><<<grid, 256, 0, h->stream>>>(h->spin, h->g, d); break;
+    case SPK_SC_26N: site_energy_kernel<SPK_SC_26N><<<grid, 256, 0, h->stream>>>(h->spin, h->g, d); break;
+  }
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host, d, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail("site energy: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -71,6 +71,15 @@ class LatticeSweep:
     def randomize(self, seed, lo, hi):
         _lib.check(self.L.spk_cuda_randomize(self.h, seed, lo, hi))
 
+    def set_site_range(self, park_seed, lo, hi):
+        """`set site range lo hi` with the reference's own Park-Miller stream (state park_seed)."""
+        _lib.check(self.L.spk_cuda_set_site_range(self.h, int(park_seed), int(lo), int(hi)))
+
+    def site_energy(self):
+        out = np.empty(self.nlocal, dtype=np.uint8)
+        _lib.check(self.L.spk_cuda_site_energy(self.h, out.ctypes.data_as(C.c_void_p), self.nlocal))
+        return out
+
     def pin_random(self, seed, fraction):
         _lib.check(self.L.spk_cuda_pin_random(self.h, seed, fraction))
 

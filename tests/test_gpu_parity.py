@@ -392,3 +392,50 @@ def test_large_lattices_bit_exact_vs_oracle(model, lat, n, q, T):
     s.sweeps(0, 2)
     assert np.array_equal(s.download(), want)
     assert s.counters() == (nacc, 2 * o.nsites)
+
+
+@pytest.mark.parametrize("model,lat,n,q", [
+    ("ising", "sq/4n", (50, 50, 1), 2),          # examples/ising/in.ising: `set site range 1 2`
+    ("potts", "tri", (30, 22, 1), 1000),
+    ("potts/neighonly", "sc/26n", (20, 14, 12), 10000),
+    ("potts/pin", "sc/6n", (12, 10, 8), 50),
+], ids=lambda v: str(v).replace(" ", ""))
+def test_device_set_site_range_is_the_reference_stream(model, lat, n, q):
+    """spk_cuda_set_site_range reproduces `set site range 1 Q` value for value: the one Park-Miller
+    stream of src/set.cpp:617-627 (the oracle's restatement of it replays the shipped logs'
+    time-0 energies, tests/test_oracle_golden.py) evaluated per site with a modular power."""
+    o = O.Oracle(model, lat, n[0], n[1], n[2], q, 0.5)
+    for master_seed in (56789, 4711):
+        m = O.mars(master_seed)
+        want = o.set_site_range(1, q, m)
+        m = O.mars(master_seed)
+        park = int(O.lib().orc_mars_uniform(O.C.byref(m)) * O.IM) or 1   # new RandomPark(ranmaster->uniform())
+        s = _sweep(model, lat, n, q, 0.5)
+        s.set_site_range(park, 1, q)
+        assert np.array_equal(s.download(), want)
+        assert s.energy() == o.total_energy(want)
+        # per-site energies (dump ... energy)
+        e = s.site_energy()
+        assert e.sum() == o.total_energy(want)
+        for site in (0, 1, o.nsites // 2, o.nsites - 1):
+            assert e[site] == O.lib().orc_site_energy(o.ctx, want.ctypes.data_as(O.C.POINTER(O.C.c_int32)), site)
+        s.close()
+
+
+def test_device_set_site_range_large_offsets():
+    """draw numbers far along the stream (modular power with a 31-bit exponent and beyond): the last
+    sites of a 2^27-site lattice against the sequential stream advanced on the host."""
+    n = (512, 512, 512)
+    s = _sweep("potts", "sc/26n", n, 50000, 0.0)
+    s.set_site_range(123456789, 1, 50000)
+    got = s.download()
+    state, IM = 123456789, O.IM
+    for i in range(1000):
+        state = state * 16807 % IM
+        assert got[i] == min(int(state * (1.0 / IM) * 50000), 49999) + 1, i
+    N = got.size
+    state = 123456789 * pow(16807, N - 1000, IM) % IM
+    for i in range(N - 1000, N):
+        state = state * 16807 % IM
+        assert got[i] == min(int(state * (1.0 / IM) * 50000), 49999) + 1, i
+    s.close()

@@ -280,3 +280,19 @@ run 0.0
     # the final `run 0.0` adds the host-side energy of the downloaded lattice: equal to the device's
     assert ra[-1][4] == ra[-1][5]
     assert re.search(r"CUDA sweep loop: .* Gsites/s", a)
+
+
+def test_cuda_set_site_range_equals_set_site_range():
+    """`cuda_set site range 1 Q` initialises the lattice on the device with the reference's own
+    stream: the whole color/strict table (time-0 energy included) equals the reference's run of
+    the script with `set site range 1 Q`, and a following `set`-dependent draw (the strict site
+    seeds come from the same master generator) is unshifted."""
+    case = dict(STRICT_CASES[1])
+    ref_script = STRICT.format(**dict(case, app="%s %d" % (case["app"], case["q"])))
+    gpu_script = STRICT.format(**dict(case, app="%s/cuda %d" % (case["app"], case["q"]))).replace(
+        "set site range 1 %d" % case["hi"], "cuda_set site range 1 %d" % case["hi"])
+    assert "cuda_set" in gpu_script
+    ref = stats_rows(run(SPK_REF, ref_script))
+    out = run(SPK_CUDA, gpu_script)
+    assert "%d settings made for site" % (16 * 8 * 12) in out
+    assert stats_rows(out) == ref and len(ref) >= 4
