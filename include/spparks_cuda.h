@@ -154,7 +154,10 @@ int spk_cuda_energy(spk_cuda_handle *h, double *energy);
  * src/app_lattice.cpp:1187-1201): connected components of equal-spin sites over the lattice's
  * neighbour stencil, computed on the device.  ncluster, mean_volume (<N>) and mean_radius (<R> =
  * mean of volume^(1/dimension)) are the three columns DiagCluster::stats prints
- * (src/diag_cluster.cpp:894-897).  Single-GPU handles (nranks == 1) with fewer than 2^32 sites. */
+ * (src/diag_cluster.cpp:894-897).  Fewer than 2^32 sites per GPU.  With several slabs (after
+ * spk_cuda_comm_init; collective: every rank calls it) the per-slab clusters are merged across the
+ * slab boundaries with 64-bit global labels (src/diag_cluster.cpp:259-285, 372-396) and every rank
+ * receives the statistics of the whole lattice. */
 int spk_cuda_cluster_stats(spk_cuda_handle *h, int64_t *ncluster, double *mean_volume, double *mean_radius);
 /* the per-site cluster ids (1-based, the reference's numbering: clusters in the order of their
  * lowest site index, as the scan of analyze_clusters opens them) and the volume of every cluster

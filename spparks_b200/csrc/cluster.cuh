@@ -61,9 +61,11 @@ __global__ void __launch_bounds__(256) cluster_init_kernel(uint32_t *label, uint
 }
 
 // one thread per site: join with every equal-spin neighbour of higher index (fully periodic lattice)
+// slab_open: the last dimension is cut into slabs (multi-GPU): no periodic wrap there, the
+// links across slab boundaries are made by cluster_boundary_kernel
 template <int LAT>
 __global__ void __launch_bounds__(256) cluster_link_kernel(const int32_t *__restrict__ spin, uint32_t *label, int X, int Y,
-                                                           int Z) {
+                                                           int Z, int slab_open) {
   using L = Lat<LAT>;
   constexpr int NN = L::NN, NB = L::NB;
   const long long n = (long long)X * Y * Z * NB;
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(256) cluster_link_kernel(const int32_t *__rest
       for (int q = 0; q < NN; q++) {
         const Off o = L::off(M, q);
         int ii = i + o.dx, jj = j + o.dy, kk = k + o.dz;
+        if (slab_open && (L::DIM == 3 ? (kk < 0 || kk >= Z) : (jj < 0 || jj >= Y))) continue;
         ii = ii < 0 ? ii + X : (ii >= X ? ii - X : ii);
         jj = jj < 0 ? jj + Y : (jj >= Y ? jj - Y : jj);
         kk = kk < 0 ? kk + Z : (kk >= Z ? kk - Z : kk);
@@ -217,8 +220,124 @@ __global__ void __launch_bounds__(256) cluster_ids_kernel(const uint32_t *label,
 }
 
 template <int LAT>
-inline void launch_cluster_link(cudaStream_t st, const int32_t *spin, uint32_t *label, int X, int Y, int Z) {
-  cluster_link_kernel<LAT><<<148 * 16, 256, 0, st>>>(spin, label, X, Y, Z);
+inline void launch_cluster_link(cudaStream_t st, const int32_t *spin, uint32_t *label, int X, int Y, int Z, int slab_open) {
+  cluster_link_kernel<LAT><<<148 * 16, 256, 0, st>>>(spin, label, X, Y, Z, slab_open);
+}
+
+// ---- clusters across slabs (multi-GPU; DiagCluster merges the per-processor clusters through
+// their boundary sites, src/diag_cluster.cpp:259-285, 372-396) ------------------------------------
+// Every local root carries a 64-bit GLOBAL label, initially its own global site index; the label
+// of a cluster is the minimum over the roots it joins across slab boundaries.  A round: pack the
+// labels of the first / last owned layer, exchange them with the ring neighbours, and lower the
+// label of every root that has an equal-spin neighbour in the adjacent ghost layer with a smaller
+// label.  Rounds repeat until no label changed on any rank.
+
+// glabel[i] = global index of i (meaningful at roots), gsize[i] = local volume (at roots)
+__global__ void __launch_bounds__(256) cluster_global_init_kernel(const uint32_t *__restrict__ label, const uint32_t *__restrict__ size,
+                                                                  unsigned long long *glabel, unsigned long long *gsize,
+                                                                  long long n, unsigned long long base) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    glabel[i] = base + (unsigned long long)i;
+    gsize[i] = label[i] == (uint32_t)i ? (unsigned long long)size[i] : 0ull;
+  }
+}
+
+// labels of the first / last owned layer (layer = plane in 3-D, row in 2-D; nl sites each)
+__global__ void __launch_bounds__(256) cluster_pack_kernel(const uint32_t *__restrict__ label, const unsigned long long *__restrict__ glabel,
+                                                           long long n, long long nl, unsigned long long *out_lo,
+                                                           unsigned long long *out_hi) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < nl; p += (long long)gridDim.x * blockDim.x) {
+    out_lo[p] = glabel[label[p]];
+    out_hi[p] = glabel[label[n - nl + p]];
+  }
+}
+
+// spin: first owned site (the adjacent ghost layers lie at [-nl, 0) and [n, n + nl))
+template <int LAT>
+__global__ void __launch_bounds__(256) cluster_boundary_kernel(const int32_t *__restrict__ spin, const uint32_t *__restrict__ label,
+                                                               unsigned long long *glabel, const unsigned long long *__restrict__ ghost_lo,
+                                                               const unsigned long long *__restrict__ ghost_hi, int X, int Y, int Z,
+                                                               int *changed) {
+  using L = Lat<LAT>;
+  constexpr int NN = L::NN, NB = L::NB;
+  const long long nl = L::DIM == 3 ? (long long)X * Y * NB : (long long)X * NB;
+  const long long n = (long long)X * Y * Z * NB;
+  int any = 0;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < 2 * nl; q += (long long)gridDim.x * blockDim.x) {
+    const int side = q >= nl;                 // 0: first layer looks down, 1: last layer looks up
+    const long long p = side ? q - nl : q;    // index inside the layer
+    const long long s = side ? n - nl + p : p;
+    const int m = (int)(p % NB);
+    const long long c = p / NB;
+    const int i = (int)(c % X), j = L::DIM == 3 ? (int)(c / X) : 0;
+    const int mine = spin[s];
+    unsigned long long best = ~0ull;
+    auto visit = [&](auto MM) {
+      constexpr int M = decltype(MM)::value;
+#pragma unroll
+      for (int t = 0; t < NN; t++) {
+        const Off o = L::off(M, t);
+        const int ds = L::DIM == 3 ? o.dz : o.dy;  // step along the slab dimension
+        if (ds != (side ? 1 : -1)) continue;
+        int ii = i + o.dx, jj = j + (L::DIM == 3 ? o.dy : 0);
+        ii = ii < 0 ? ii + X : (ii >= X ? ii - X : ii);
+        if (L::DIM == 3) jj = jj < 0 ? jj + Y : (jj >= Y ? jj - Y : jj);
+        const long long g = ((long long)jj * X + ii) * NB + o.m;  // index inside the ghost layer
+        const int theirs = side ? spin[n + g] : spin[g - nl];
+        if (theirs == mine) {
+          const unsigned long long gl = side ? ghost_hi[g] : ghost_lo[g];
+          best = gl < best ? gl : best;
+        }
+      }
+    };
+    if (NB == 2 && m == 1) visit(std::integral_constant<int, 1>{});
+    else visit(std::integral_constant<int, 0>{});
+    if (best != ~0ull) {
+      const unsigned long long old = atomicMin(glabel + label[s], best);
+      any |= best < old;
+    }
+  }
+  if (any) *changed = 1;
+}
+
+// roots whose cluster is represented by another root (glabel != own index): (glabel, volume) pairs
+__global__ void __launch_bounds__(256) cluster_foreign_kernel(const uint32_t *__restrict__ label, const unsigned long long *__restrict__ glabel,
+                                                              const unsigned long long *__restrict__ gsize, long long n,
+                                                              unsigned long long base, unsigned long long *pairs, int *count,
+                                                              int capacity) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (label[i] == (uint32_t)i && glabel[i] != base + (unsigned long long)i) {
+      const int slot = atomicAdd(count, 1);
+      if (slot < capacity) { pairs[2 * slot] = glabel[i]; pairs[2 * slot + 1] = gsize[i]; }
+    }
+}
+
+// add the volumes of the gathered foreign roots whose representative lives in this slab
+__global__ void __launch_bounds__(256) cluster_absorb_kernel(const unsigned long long *__restrict__ pairs, long long npairs,
+                                                             unsigned long long base, long long n, unsigned long long *gsize) {
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < npairs; q += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long gl = pairs[2 * q];
+    if (gl != ~0ull && gl >= base && gl < base + (unsigned long long)n) atomicAdd(gsize + (gl - base), pairs[2 * q + 1]);
+  }
+}
+
+// clusters represented in this slab and their radius sum
+__global__ void __launch_bounds__(256) cluster_global_stats_kernel(const uint32_t *__restrict__ label, const unsigned long long *__restrict__ glabel,
+                                                                   const unsigned long long *__restrict__ gsize, long long n,
+                                                                   unsigned long long base, double invdim, unsigned long long *ncluster,
+                                                                   double *rsum) {
+  unsigned long long cnt = 0;
+  double r = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (label[i] == (uint32_t)i && glabel[i] == base + (unsigned long long)i) {
+      cnt++;
+      r += pow((double)gsize[i], invdim);
+    }
+  for (int o = 16; o; o >>= 1) {
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    r += __shfl_down_sync(0xffffffffu, r, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt) { atomicAdd(ncluster, cnt); atomicAdd(rsum, r); }
 }
 
 }  // namespace spk

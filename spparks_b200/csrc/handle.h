@@ -51,6 +51,10 @@ struct spk_cuda_handle {
   uint32_t *cl_label = nullptr, *cl_size = nullptr;  // diag_style cluster: union-find parents, volumes / ids per root
   uint32_t *cl_blocksum = nullptr;
   unsigned long long *cl_count = nullptr;             // [0] ncluster, [1] (as double) sum of radii
+  // clusters across slabs: 64-bit global labels / merged volumes per local root, boundary-layer
+  // label buffers (out_lo, out_hi, ghost_lo, ghost_hi), foreign-root pairs, flags
+  unsigned long long *cl_glabel = nullptr, *cl_gsize = nullptr, *cl_layer = nullptr, *cl_pairs = nullptr;
+  int *cl_flags = nullptr;                            // [0] a label changed this round, [1] number of foreign roots
   int32_t *edge = nullptr;     // tile-edge words of the colour-pair launches (StreamMap::edge)
   size_t edge_words = 0;
   bool use_pair = false;       // SPK_CUDA_PAIR=1: sc/26n colour pairs in one launch (half the DRAM traffic; measured slower)

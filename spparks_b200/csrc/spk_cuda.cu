@@ -57,6 +57,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 } g_nccl;
 
@@ -69,7 +70,7 @@ int nccl_bind() {
   *(void **)(&g_nccl.name) = dlsym(dl, "nccl" #name);                       \
   if (!g_nccl.name) return fail("NCCL symbol nccl" #name " not found")
   BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(GroupStart); BIND(GroupEnd);
-  BIND(Send); BIND(Recv); BIND(AllGather); BIND(GetErrorString);
+  BIND(Send); BIND(Recv); BIND(AllGather); BIND(AllReduce); BIND(GetErrorString);
 #undef BIND
   g_nccl.dl = dl;
   return 0;
@@ -483,6 +484,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   if (h->kstat_host) cudaFreeHost(h->kstat_host);
   if (h->ev_kstat) cudaEventDestroy(h->ev_kstat);
   cudaFree(h->cl_label); cudaFree(h->cl_size); cudaFree(h->cl_blocksum); cudaFree(h->cl_count);
+  cudaFree(h->cl_glabel); cudaFree(h->cl_gsize); cudaFree(h->cl_layer); cudaFree(h->cl_pairs); cudaFree(h->cl_flags);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->mask_base);
   cudaFree(h->base); cudaFree(h->base_alt); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
@@ -1117,12 +1119,20 @@ static int check_halo_timeout(spk_cuda_handle *h) {
 }
 
 // union-find over the current lattice: labels flattened to roots, volumes per root, ncluster and
-// the radius sum on the device; returns ncluster and the radius sum
+// the radius sum on the device; returns ncluster and the radius sum (of the WHOLE lattice: with
+// several slabs the clusters are merged across the slab boundaries and the sums reduced over ranks)
+static int cluster_across_slabs(spk_cuda_handle *h, unsigned long long *ncluster, double *rsum);
+
 static int cluster_analyse(spk_cuda_handle *h, unsigned long long *ncluster, double *rsum) {
-  if (h->d.nranks != 1) return fail("cluster analysis across slabs is not implemented (nranks must be 1)");
-  if (h->nlocal >= (int64_t)1 << 32) return fail("cluster analysis needs fewer than 2^32 sites");
+  if (h->nlocal >= (int64_t)1 << 32) return fail("cluster analysis needs fewer than 2^32 sites per GPU");
   CU(cudaSetDevice(h->d.device));
   const long long n = h->nlocal;
+  const bool multi = h->d.nranks > 1;
+  if (multi) {
+    if (!h->comm) return fail("spk_cuda_comm_init has not been called");
+    const int rc = spk_cuda_halo_exchange(h);  // DiagCluster: comm->all() first (src/diag_cluster.cpp:262)
+    if (rc) return rc;
+  }
   if (!h->cl_label) {
     CU(cudaMalloc(&h->cl_label, (size_t)n * sizeof(uint32_t)));
     CU(cudaMalloc(&h->cl_size, (size_t)n * sizeof(uint32_t)));
@@ -1131,19 +1141,107 @@ static int cluster_analyse(spk_cuda_handle *h, unsigned long long *ncluster, dou
   }
   const int grid = 148 * 16;
   cluster_init_kernel<<<grid, 256, 0, h->stream>>>(h->cl_label, h->cl_size, n);
-  const int X = h->g.gX, Y = h->g.gY, Z = h->dim == 3 ? h->g.gZ : 1;
+  const int X = h->g.X, Y = h->g.Y, Z = h->dim == 3 ? h->g.Z : 1;  // local extents (= global on one GPU)
   switch (h->d.lattice) {
-    case SPK_SQ_4N: launch_cluster_link<SPK_SQ_4N>(h->stream, h->spin, h->cl_label, X, Y, Z); break;
-    case SPK_SQ_8N: launch_cluster_link<SPK_SQ_8N>(h->stream, h->spin, h->cl_label, X, Y, Z); break;
-    case SPK_TRI: launch_cluster_link<SPK_TRI>(h->stream, h->spin, h->cl_label, X, Y, Z); break;
-    case SPK_SC_6N: launch_cluster_link<SPK_SC_6N>(h->stream, h->spin, h->cl_label, X, Y, Z); break;
-    case SPK_SC_26N: launch_cluster_link<SPK_SC_26N>(h->stream, h->spin, h->cl_label, X, Y, Z); break;
+    case SPK_SQ_4N: launch_cluster_link<SPK_SQ_4N>(h->stream, h->spin, h->cl_label, X, Y, Z, multi); break;
+    case SPK_SQ_8N: launch_cluster_link<SPK_SQ_8N>(h->stream, h->spin, h->cl_label, X, Y, Z, multi); break;
+    case SPK_TRI: launch_cluster_link<SPK_TRI>(h->stream, h->spin, h->cl_label, X, Y, Z, multi); break;
+    case SPK_SC_6N: launch_cluster_link<SPK_SC_6N>(h->stream, h->spin, h->cl_label, X, Y, Z, multi); break;
+    case SPK_SC_26N: launch_cluster_link<SPK_SC_26N>(h->stream, h->spin, h->cl_label, X, Y, Z, multi); break;
     default: return fail("unknown lattice %d", h->d.lattice);
   }
   cluster_flatten_kernel<<<grid, 256, 0, h->stream>>>(h->cl_label, h->cl_size, n);
+  h->launches += 3;
+  if (multi) return cluster_across_slabs(h, ncluster, rsum);
   CU(cudaMemsetAsync(h->cl_count, 0, 2 * sizeof(unsigned long long), h->stream));
   cluster_stats_kernel<<<grid, 256, 0, h->stream>>>(h->cl_label, h->cl_size, n, 1.0 / h->dim, h->cl_count,
                                                     reinterpret_cast<double *>(h->cl_count + 1));
+  h->launches++;
+  CU(cudaGetLastError());
+  unsigned long long out[2];
+  CU(cudaMemcpyAsync(out, h->cl_count, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *ncluster = out[0];
+  memcpy(rsum, &out[1], sizeof(double));
+  return 0;
+}
+
+// Merge of the per-slab clusters (cluster.cuh: "clusters across slabs"): rounds of boundary-label
+// exchange with the ring neighbours until no global label changes anywhere, then the volumes of
+// the roots represented elsewhere are gathered and absorbed by their representatives, and the two
+// sums are reduced over the ranks (the analogue of DiagCluster's merge on the root process,
+// src/diag_cluster.cpp:372-396, without funnelling anything through one rank).
+static int cluster_across_slabs(spk_cuda_handle *h, unsigned long long *ncluster, double *rsum) {
+  const long long n = h->nlocal, nl = h->plane;  // nl = sites of one layer of the slab dimension
+  const unsigned long long base = (unsigned long long)h->g.g0 * (unsigned long long)h->plane;
+  const int nr = h->d.nranks, lower = (h->d.rank + nr - 1) % nr, upper = (h->d.rank + 1) % nr;
+  const int cap = (int)std::min<long long>(2 * nl, 1 << 30);
+  if (!h->cl_glabel) {
+    CU(cudaMalloc(&h->cl_glabel, (size_t)n * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->cl_gsize, (size_t)n * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->cl_layer, (size_t)4 * nl * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->cl_pairs, (size_t)2 * cap * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->cl_flags, 4 * sizeof(int)));
+  }
+  unsigned long long *out_lo = h->cl_layer, *out_hi = out_lo + nl, *ghost_lo = out_hi + nl, *ghost_hi = ghost_lo + nl;
+  const int grid = 148 * 16, lgrid = (int)std::min<long long>(148 * 8, (2 * nl + 255) / 256);
+  cluster_global_init_kernel<<<grid, 256, 0, h->stream>>>(h->cl_label, h->cl_size, h->cl_glabel, h->cl_gsize, n, base);
+  h->launches++;
+  const int X = h->g.X, Y = h->g.Y, Z = h->dim == 3 ? h->g.Z : 1;
+  for (int round = 0;; round++) {
+    if (round > 4 * nr + 64) return fail("cluster merge across slabs did not converge");
+    CU(cudaMemsetAsync(h->cl_flags, 0, sizeof(int), h->stream));
+    cluster_pack_kernel<<<lgrid, 256, 0, h->stream>>>(h->cl_label, h->cl_glabel, n, nl, out_lo, out_hi);
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.Send(out_lo, (size_t)nl, ncclUint64, lower, h->comm, h->stream));
+    NC(g_nccl.Send(out_hi, (size_t)nl, ncclUint64, upper, h->comm, h->stream));
+    NC(g_nccl.Recv(ghost_hi, (size_t)nl, ncclUint64, upper, h->comm, h->stream));
+    NC(g_nccl.Recv(ghost_lo, (size_t)nl, ncclUint64, lower, h->comm, h->stream));
+    NC(g_nccl.GroupEnd());
+    switch (h->d.lattice) {
+#define SPK_CB(LATV) case LATV: cluster_boundary_kernel<LATV><<<lgrid, 256, 0, h->stream>>>(h->spin, h->cl_label, h->cl_glabel, ghost_lo, ghost_hi, X, Y, Z, h->cl_flags); break;
+      SPK_CB(SPK_SQ_4N) SPK_CB(SPK_SQ_8N) SPK_CB(SPK_TRI) SPK_CB(SPK_SC_6N) SPK_CB(SPK_SC_26N)
+#undef SPK_CB
+      default: return fail("unknown lattice %d", h->d.lattice);
+    }
+    NC(g_nccl.AllReduce(h->cl_flags, h->cl_flags, 1, ncclInt32, ncclMax, h->comm, h->stream));
+    h->launches += 4;
+    int changed = 0;
+    CU(cudaMemcpyAsync(&changed, h->cl_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (!changed) break;
+  }
+  // volumes of the roots represented elsewhere -> every rank -> absorbed by the representatives
+  CU(cudaMemsetAsync(h->cl_flags + 1, 0, sizeof(int), h->stream));
+  cluster_foreign_kernel<<<grid, 256, 0, h->stream>>>(h->cl_label, h->cl_glabel, h->cl_gsize, n, base, h->cl_pairs,
+                                                      h->cl_flags + 1, cap);
+  CU(cudaMemcpyAsync(h->cl_flags + 2, h->cl_flags + 1, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  NC(g_nccl.AllReduce(h->cl_flags + 2, h->cl_flags + 2, 1, ncclInt32, ncclMax, h->comm, h->stream));
+  int counts[2] = {0, 0};  // mine, maximum over the ranks
+  CU(cudaMemcpyAsync(counts, h->cl_flags + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (counts[0] > cap) return fail("cluster merge: %d boundary roots exceed the buffer of %d", counts[0], cap);
+  if (counts[1] > 0) {
+    const size_t per = (size_t)2 * counts[1];  // padded to the largest list; unused slots carry label ~0
+    unsigned long long *all = nullptr;
+    CU(cudaMalloc(&all, per * nr * sizeof(unsigned long long)));
+    if (counts[0] < counts[1])
+      CU(cudaMemsetAsync(h->cl_pairs + 2 * (size_t)counts[0], 0xFF, (size_t)2 * (counts[1] - counts[0]) * sizeof(unsigned long long), h->stream));
+    ncclResult_t r = g_nccl.AllGather(h->cl_pairs, all, per, ncclUint64, h->comm, h->stream);
+    if (r == ncclSuccess) {
+      const long long np = (long long)counts[1] * nr;
+      cluster_absorb_kernel<<<(int)std::min<long long>(148 * 8, (np + 255) / 256), 256, 0, h->stream>>>(all, np, base, n, h->cl_gsize);
+      cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(all);
+    if (r != ncclSuccess) return fail("ncclAllGather: %s", g_nccl.GetErrorString(r));
+    h->launches += 2;
+  }
+  CU(cudaMemsetAsync(h->cl_count, 0, 2 * sizeof(unsigned long long), h->stream));
+  cluster_global_stats_kernel<<<grid, 256, 0, h->stream>>>(h->cl_label, h->cl_glabel, h->cl_gsize, n, base, 1.0 / h->dim,
+                                                           h->cl_count, reinterpret_cast<double *>(h->cl_count + 1));
+  NC(g_nccl.AllReduce(h->cl_count, h->cl_count, 1, ncclUint64, ncclSum, h->comm, h->stream));
+  NC(g_nccl.AllReduce(h->cl_count + 1, h->cl_count + 1, 1, ncclDouble, ncclSum, h->comm, h->stream));
   h->launches += 4;
   CU(cudaGetLastError());
   unsigned long long out[2];
@@ -1162,13 +1260,14 @@ int spk_cuda_cluster_stats(spk_cuda_handle *h, int64_t *ncluster, double *mean_v
   if (rc) return rc;
   if (ncluster) *ncluster = (int64_t)nc;
   // volsum = every site is in exactly one cluster (src/diag_cluster.cpp:595-605)
-  if (mean_volume) *mean_volume = (double)h->nlocal / (double)nc;
+  if (mean_volume) *mean_volume = (double)h->nglobal / (double)nc;
   if (mean_radius) *mean_radius = rsum / (double)nc;
   return 0;
 }
 
 int spk_cuda_cluster_ids(spk_cuda_handle *h, int32_t *ids, int64_t *volumes, int64_t nvolumes) {
   if (!h) return fail("null handle");
+  if (h->d.nranks != 1) return fail("per-site cluster ids are a single-GPU facility (nranks must be 1); the statistics work across slabs");
   unsigned long long nc = 0;
   double rsum = 0.0;
   int rc = cluster_analyse(h, &nc, &rsum);

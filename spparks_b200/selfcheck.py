@@ -70,6 +70,7 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
             dist.all_gather(parts, mine)
             acc = torch.tensor(list(s.counters()) + [s.energy()], dtype=torch.float64, device="cuda")
             dist.all_reduce(acc)
+            clus = s.cluster_stats()  # collective: clusters merged across the slab boundaries
             if rank == 0 and fail is None:
                 got = torch.cat(parts).cpu().numpy()
                 one = LatticeSweep(model, lat, n[0], n[1], n[2], nspins=q, temperature=T, seed=777, device=local)
@@ -82,6 +83,10 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
                     fail = "counters differ"
                 elif float(acc[2]) != one.energy():
                     fail = "energy differs"
+                else:
+                    c1 = one.cluster_stats()
+                    if clus[0] != c1[0] or clus[1] != c1[1] or abs(clus[2] - c1[2]) > 1e-9 * c1[2]:
+                        fail = "cluster statistics %r differ from the 1-GPU run's %r" % (clus, c1)
                 one.close()
             s.close()
             flag = torch.tensor([0 if fail is None else 1], dtype=torch.int32, device="cuda")
@@ -91,6 +96,39 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
             if int(flag.item()):
                 verdict = "%s %s %s halo=%s: %s" % (model, lat, "x".join(map(str, n)), halo, fail or "failed on rank 0")
                 break
+        # clusters that cross every slab boundary and wrap around the periodic box: diagonal bands and
+        # one percolating background, no sweeps (pure test of the cross-slab merge)
+        for lat, n in (("sc/26n", (16, 12, max(16, 2 * world))), ("sq/4n", (40, max(32, 4 * world), 1)), ("tri", (24, max(32, 4 * world), 1))):
+            if verdict != "ok":
+                break
+            dim3 = lat.startswith("sc")
+            nb = NBASIS.get(lat, 1)
+            zz, yy, xx, mm = np.meshgrid(np.arange(n[2]), np.arange(n[1]), np.arange(n[0]), np.arange(nb), indexing="ij")
+            slab = zz if dim3 else yy
+            spins = np.where((xx + 3 * slab) % 8 < 3, 2 + (xx + 3 * slab) // 8 % 3, 1).astype(np.int32).reshape(-1)
+            s = LatticeSweep("potts", lat, n[0], n[1], n[2], nspins=5, temperature=0.5, seed=1, device=local, rank=rank, nranks=world)
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt = torch.frombuffer(bytearray(LatticeSweep.comm_id()), dtype=torch.uint8).cuda()
+            dist.broadcast(idt, 0)
+            s.comm_init(idt.cpu().numpy().tobytes())
+            s.upload(spins[rank * s.nlocal:(rank + 1) * s.nlocal])
+            clus = s.cluster_stats()
+            s.close()
+            fail = None
+            if rank == 0:
+                one = LatticeSweep("potts", lat, n[0], n[1], n[2], nspins=5, temperature=0.5, seed=1, device=local)
+                one.upload(spins)
+                c1 = one.cluster_stats()
+                one.close()
+                if clus[0] != c1[0] or clus[1] != c1[1] or abs(clus[2] - c1[2]) > 1e-9 * c1[2]:
+                    fail = "cluster statistics %r differ from the 1-GPU run's %r" % (clus, c1)
+            flag = torch.tensor([0 if fail is None else 1], dtype=torch.int32, device="cuda")
+            dist.broadcast(flag, 0)
+            if log and rank == 0:
+                log("%s banded clusters %s %s ranks %d: %r" % ("ok" if fail is None else "FAIL", lat, n, world, clus))
+            if int(flag.item()):
+                verdict = "banded clusters %s: %s" % (lat, fail or "failed on rank 0")
     finally:
         if old is None:
             os.environ.pop("SPK_CUDA_NO_P2P", None)
