@@ -165,7 +165,14 @@ int spk_cuda_cluster_stats(spk_cuda_handle *h, int64_t *ncluster, double *mean_v
  * either pointer may be NULL.  Runs the analysis itself. */
 int spk_cuda_cluster_ids(spk_cuda_handle *h, int32_t *ids, int64_t *volumes, int64_t nvolumes);
 
-/* multi-GPU: one process per GPU; rank 0 creates the id, the host broadcasts it (MPI_Bcast in
+/* Multi-GPU calls are COLLECTIVE, like their MPI counterparts in the reference: every rank makes
+ * the same calls in the same order.  That includes the calls that replace or expose the spins
+ * (upload_spins, randomize, set_site_range, pin_random, device_spins, sweep_color*): they mark the
+ * ghost layers stale, and spk_cuda_sweeps re-seeds them with one exchange in which all ranks take
+ * part; and the calls that read the ghost layers (energy, site_energy, cluster_stats), which end
+ * with a handshake so that no neighbour's next sweep can overtake a slower rank's read.
+ *
+ * multi-GPU: one process per GPU; rank 0 creates the id, the host broadcasts it (MPI_Bcast in
  * the plugin, torch.distributed in bench.py), every rank joins.  Replaces CommLattice::init
  * (src/comm_lattice.cpp:74-135). */
 #define SPK_CUDA_COMM_ID_BYTES 128

@@ -38,7 +38,9 @@ class DiagClusterCuda : public Diag {
   {
     host = dynamic_cast<SpkCudaHost *>(app);
     if (!host) error->all(FLERR,"diag_style cluster/cuda requires an app_style <name>/cuda");
-    if (nprocs > 1) error->all(FLERR,"diag_style cluster/cuda is serial (one GPU) only");
+    // several ranks: the library merges the per-slab clusters across the slab boundaries and
+    // hands every rank the statistics of the whole lattice (compute() is collective, as
+    // DiagCluster::compute is, src/diag_cluster.cpp:230-260)
   }
 
   void compute()

@@ -574,6 +574,8 @@ int spk_cuda_set_site_range(spk_cuda_handle *h, int32_t park_seed, int32_t lo, i
   return 0;
 }
 
+static int p2p_read_fence(spk_cuda_handle *h);
+
 int spk_cuda_site_energy(spk_cuda_handle *h, unsigned char *host, int64_t n) {
   if (!h || !host) return fail("null argument");
   if (n != h->nlocal) return fail("site energies of %lld sites, slab owns %lld", (long long)n, (long long)h->nlocal);
@@ -593,6 +595,7 @@ int spk_cuda_site_energy(spk_cuda_handle *h, unsigned char *host, int64_t n) {
   }
   h->launches++;
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && p2p_read_fence(h)) e = cudaErrorUnknown;
   if (e == cudaSuccess) e = cudaMemcpyAsync(host, d, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   cudaFree(d);
@@ -999,6 +1002,21 @@ int spk_cuda_neigh_variant(spk_cuda_handle *h, int *variant, double *mean_distin
   return 0;
 }
 
+// Peer-memory halo: a call that READS the ghost layers outside spk_cuda_sweeps (energy, clusters,
+// per-site energies) must not return while a faster neighbour could already be storing the next
+// sweep's boundary values into them.  One more signal / wait step on the flag words closes the
+// window: when it completes, both neighbours have finished their own reads.  Like every multi-rank
+// entry point these calls are collective (every rank makes them, in the same order).
+static int p2p_read_fence(spk_cuda_handle *h) {
+  if (h->d.nranks == 1 || !h->p2p || !h->flags) return 0;
+  const uint32_t t = ++h->step;
+  halo_signal_kernel<<<1, 32, 0, h->stream>>>(h->peer_flags[0], h->peer_flags[1], t);
+  halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->flags, t);
+  h->launches += 2;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int spk_cuda_energy(spk_cuda_handle *h, double *energy) {
   if (!h || !energy) return fail("null argument");
   CU(cudaSetDevice(h->d.device));
@@ -1007,6 +1025,7 @@ int spk_cuda_energy(spk_cuda_handle *h, double *energy) {
   CU(cudaMemsetAsync(h->escratch, 0, sizeof(unsigned long long), h->stream));
   rc = launch_energy(h->d.lattice, h->stream, h->spin, h->g, h->escratch, &h->launches);
   if (rc) return fail("energy kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (p2p_read_fence(h)) return 1;
   unsigned long long e = 0;
   CU(cudaMemcpyAsync(&e, h->escratch, sizeof e, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -1242,6 +1261,7 @@ static int cluster_across_slabs(spk_cuda_handle *h, unsigned long long *ncluster
                                                            h->cl_count, reinterpret_cast<double *>(h->cl_count + 1));
   NC(g_nccl.AllReduce(h->cl_count, h->cl_count, 1, ncclUint64, ncclSum, h->comm, h->stream));
   NC(g_nccl.AllReduce(h->cl_count + 1, h->cl_count + 1, 1, ncclDouble, ncclSum, h->comm, h->stream));
+  // (the all-reduces order every rank's ghost reads before anybody's next sweep: no extra fence)
   h->launches += 4;
   CU(cudaGetLastError());
   unsigned long long out[2];

@@ -45,6 +45,33 @@ def test_ising_2d_matches_onsager(T):
     assert abs(m - m_exact) < 0.005 + (0.01 if m_exact == 0.0 else 0.0), (T, m, m_exact)
 
 
+@pytest.mark.parametrize("T", [1.10, 1.17])
+def test_ising_2d_energy_near_tc_matches_onsager(T):
+    """Either side of T_c = 1.1346 on 4096^2: the energy is exact at any T (Onsager) and its finite-size
+    correction at L = 4096 is far below the tolerance; the magnetisation is only checked below T_c
+    (1.10: |m| = 0.789), above it the finite-size tail at 3 % from T_c is not negligible.  Ordered start,
+    long equilibration (the correlation length is ~20-30 lattice constants at these temperatures)."""
+    from spparks_b200 import LatticeSweep
+    L = 4096
+    s = LatticeSweep("ising", "sq/4n", L, L, 1, temperature=T, seed=777)
+    s.upload(np.ones(L * L, dtype=np.int32))
+    s.sweeps(0, 20000)
+    es, ms, sweep = [], [], 20000
+    for _ in range(40):
+        s.sweeps(sweep, 500)
+        sweep += 500
+        es.append(s.energy() / (L * L))
+        if T < 1.1346:
+            a = s.download()
+            ms.append(abs(2.0 * np.count_nonzero(a == 1) / a.size - 1.0))
+    m_exact, e_exact = onsager(T)
+    e = float(np.mean(es))
+    # tolerance 0.3 % of the energy: the spread of the 40 samples is ~1e-4 at this size
+    assert abs(e - e_exact) < 0.003 * e_exact, (T, e, e_exact, float(np.std(es)))
+    if ms:
+        assert abs(float(np.mean(ms)) - m_exact) < 0.01, (T, float(np.mean(ms)), m_exact)
+
+
 def test_potts_grain_growth_follows_reference_curve():
     """potts/neighonly Q=10000 on sc/26n at T=0.5 from a random start: mean grain volume
     N/ncluster and energy per site versus MCS against the unmodified reference (3 seeds of 96^3,
