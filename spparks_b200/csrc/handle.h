@@ -76,6 +76,16 @@ struct spk_cuda_handle {
   int64_t nattempt_base = 0;     // attempts before the last spk_cuda_reset_counters
   int64_t kstat_attempt0 = 0;    // nattempt_base + nattempt when the statistic was last reset
   double kstat_mean = -1.0;      // last mean read back (-1: none yet)
+  // 16-bit shadow of the lattice (sweep_stream16.cuh): sc/26n potts / potts/pin with every spin
+  // <= 65534 sweep on it inside spk_cuda_sweeps; exactly one of the two copies may be stale
+  uint16_t *shadow_base = nullptr, *shadow = nullptr;  // allocation incl. the two ghost planes, first owned site
+  CUtensorMap tmap16;
+  bool shadow_ok = false;       // usable (eligible handle, allocation and tensor map succeeded; SPK_CUDA_NO_SHADOW16=1 disables)
+  bool shadow_current = false;  // holds the current spins (incl. ghost planes when ghosts_valid)
+  bool canon_current = true;    // the int32 lattice holds the current spins
+  bool smem16_set = false;
+  void *peer_map16[2] = {nullptr, nullptr};            // the ring neighbours' shadow allocations (peer memory)
+  uint16_t *mirror16_lo = nullptr, *mirror16_hi = nullptr;
   int32_t *base_alt = nullptr;  // second lattice buffer of the out-of-place fused 2-D sweep
   CUtensorMap tmap_alt;
   // peer-memory halo (3-D slabs through the streaming kernel): the boundary launches of a colour
@@ -104,6 +114,8 @@ template <int MODEL> struct ModelEntry {
   static int sweep_set(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop);
   // colour-fused 2-D sweep (launch_tile2d): 0 launched, -1 not applicable, >0 error
   static int fused(spk_cuda_handle *h, const SweepArgs &a, int part);
+  // one colour of the box on the 16-bit shadow (launch_stream16): 0 launched, -1 not applicable, >0 error
+  static int shadow16(spk_cuda_handle *h, int color, const int32_t *box);
   // sc/26n colour pair: 0 launched, -1 not applicable, >0 error
   static int pair(spk_cuda_handle *h, int color, const int32_t *box);
 };

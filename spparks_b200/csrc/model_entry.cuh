@@ -6,6 +6,7 @@
 
 #include "handle.h"
 #include "sweep_stream.cuh"
+#include "sweep_stream16.cuh"
 #include "sweep_tile2d.cuh"
 #include "sweep_tiled.cuh"
 
@@ -223,6 +224,54 @@ template <int MODEL> int sweep_pair_m(spk_cuda_handle *h, int color, const int32
   return rc;
 }
 
+// one colour class of the (full x, y) box on the 16-bit shadow: 0 launched, -1 not applicable, >0 error
+template <int MODEL> int launch_stream16(spk_cuda_handle *h, int color, const int32_t *box) {
+  if constexpr (MODEL != SPK_POTTS && MODEL != SPK_POTTS_PIN) {
+    return -1;
+  } else {
+    using C = Stream16Cfg;
+    if (!h->shadow_ok || h->d.lattice != SPK_SC_26N) return -1;
+    Box b;
+    if (!local_box(h, box, b)) return 0;
+    const Geo &g = h->g;
+    if (b.ilo != 0 || b.ihi != g.X || b.jlo != 0 || b.jhi != g.Y) return -1;
+    const int c0 = color - 1;
+    StreamMap sm;
+    sm.edge = nullptr;
+    sm.nrows = 0;
+    const int kfirst = b.klo + ((b.klo ^ (c0 >> 2)) & 1);
+    const int nq = kfirst < b.khi ? (b.khi - kfirst + 1) / 2 : 0;
+    h->nattempt += class_count<SPK_SC_26N>(h, b, c0);
+    if (nq <= 0) return 0;
+    sm.ntx = (g.X + S16_TX - 1) / S16_TX;
+    sm.nty = (g.Y + C::YT - 1) / C::YT;
+    sm.kfirst = kfirst;
+    sm.nq = nq;
+    static const int items_per_cta = [] { const char *e = getenv("SPK_CUDA_ITEMS_PER_CTA"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+    const int grid_max = 2 * 148;
+    int nzc = (items_per_cta * grid_max + sm.ntx * sm.nty - 1) / (sm.ntx * sm.nty);
+    if (nzc > nq) nzc = nq;
+    if (nzc < 1) nzc = 1;
+    sm.qchunk = (nq + nzc - 1) / nzc;
+    sm.nzc = (nq + sm.qchunk - 1) / sm.qchunk;
+    sm.items = sm.ntx * sm.nty * sm.nzc;
+    const int grid = sm.items < grid_max ? sm.items : grid_max;
+    Sweep16Args a;
+    a.spin = h->shadow; a.g = g; a.c0 = c0; a.ev = h->ev; a.naccept = h->naccept;
+    a.mirror_lo = h->mirror_active ? h->mirror16_lo : nullptr;
+    a.mirror_hi = h->mirror_active ? h->mirror16_hi : nullptr;
+    a.minus_one = -1;
+    auto *kern = sweep_stream16_kernel<MODEL>;
+    if (!h->smem16_set) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) return 1;
+      h->smem16_set = true;
+    }
+    kern<<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap16, a, sm);
+    h->launches++;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  }
+}
+
 template <int MODEL>
 int ModelEntry<MODEL>::sweep_set(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nloop) {
   switch (h->d.lattice) {
@@ -242,6 +291,10 @@ template <int MODEL> int ModelEntry<MODEL>::fused(spk_cuda_handle *h, const Swee
     case SPK_TRI: return launch_tile2d<SPK_TRI, MODEL>(h, a, part);
     default: return -1;
   }
+}
+
+template <int MODEL> int ModelEntry<MODEL>::shadow16(spk_cuda_handle *h, int color, const int32_t *box) {
+  return launch_stream16<MODEL>(h, color, box);
 }
 
 template <int MODEL> int ModelEntry<MODEL>::pair(spk_cuda_handle *h, int color, const int32_t *box) {

@@ -17,6 +17,7 @@
 #include "aux_kernels.cuh"
 #include "cluster.cuh"
 #include "sweep_stream.cuh"   // StreamCfg (tensor-map box shapes)
+#include "sweep_stream16.cuh" // Stream16Cfg, shadow conversion kernels
 #include "sweep_tile2d.cuh"   // Tile2dCfg
 
 namespace {
@@ -187,6 +188,30 @@ int build_tensor_map(spk_cuda_handle *h) {
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   h->stream_ok = (r == CUDA_SUCCESS);
+  // 16-bit shadow (sweep_stream16.cuh): the tensor is described in 32-bit words of two sites
+  h->shadow_ok = false;
+  {
+    const char *ns16 = getenv("SPK_CUDA_NO_SHADOW16");
+    const bool want = h->stream_ok && h->d.lattice == SPK_SC_26N && h->pk16 && h->g.X % 8 == 0 &&
+                      (h->d.model == SPK_POTTS || h->d.model == SPK_POTTS_PIN) && !(ns16 && ns16[0] == '1');
+    if (want) {
+      const size_t n16 = (size_t)(h->nlocal + 2 * h->plane);
+      if (!h->shadow_base && cudaMalloc(&h->shadow_base, n16 * sizeof(uint16_t)) != cudaSuccess) {
+        cudaGetLastError();
+        h->shadow_base = nullptr;
+      }
+      if (h->shadow_base) {
+        h->shadow = h->shadow_base + h->plane;
+        cuuint64_t d16[3] = {(cuuint64_t)h->g.X / 2, (cuuint64_t)h->g.Y, (cuuint64_t)h->nslab + 2};
+        cuuint64_t s16[2] = {(cuuint64_t)h->g.X * 2, (cuuint64_t)h->g.X * h->g.Y * 2};
+        cuuint32_t b16[3] = {(cuuint32_t)S16_BX / 2, (cuuint32_t)Stream16Cfg::RP, 1};
+        r = ((encode_fn)fn)(&h->tmap16, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, h->shadow_base, d16, s16, b16, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        h->shadow_ok = (r == CUDA_SUCCESS);
+      }
+    }
+  }
   h->tmap8_ok = false;
   if (h->stream_ok && h->d.lattice == SPK_SC_26N && neigh_like(h->d.model) && h->pk16) {
     cuuint32_t box8[3] = {(cuuint32_t)ST_BX, (cuuint32_t)StreamCfgOf<SPK_SC_26N, 1>::RP, 1};
@@ -203,6 +228,35 @@ int build_tensor_map(spk_cuda_handle *h) {
 // the mean nevent the kernels accumulate in h->kstat.  Called at the first colour of a sweep;
 // never blocks: the statistic is copied to pinned memory behind the launches already queued and
 // picked up one or two sweeps later.  Both variants give identical spins, only the speed differs.
+// ---- the two copies of an eligible lattice (int32 canonical, 16-bit shadow): exactly one may be
+// stale; conversions cover the ghost planes too, so `ghosts_valid` speaks for both
+int ensure_canon(spk_cuda_handle *h) {
+  if (h->canon_current) return 0;
+  const long long n8 = (h->nlocal + 2 * h->plane) / 8;
+  shadow_unpack_kernel<<<148 * 8, 256, 0, h->stream>>>(reinterpret_cast<const uint4 *>(h->shadow_base),
+                                                       reinterpret_cast<int4 *>(h->base), n8);
+  h->launches++;
+  CU(cudaGetLastError());
+  h->canon_current = true;
+  return 0;
+}
+int ensure_shadow(spk_cuda_handle *h) {
+  if (h->shadow_current) return 0;
+  const long long n8 = (h->nlocal + 2 * h->plane) / 8;
+  shadow_pack_kernel<<<148 * 8, 256, 0, h->stream>>>(reinterpret_cast<const int4 *>(h->base),
+                                                     reinterpret_cast<uint4 *>(h->shadow_base), n8);
+  h->launches++;
+  CU(cudaGetLastError());
+  h->shadow_current = true;
+  return 0;
+}
+// the caller is about to read (write = false) or modify (write = true) the int32 lattice
+int use_canon(spk_cuda_handle *h, bool write) {
+  if (ensure_canon(h)) return 1;
+  if (write) h->shadow_current = false;
+  return 0;
+}
+
 // the spins were replaced (upload, randomize): forget what the statistic said about the old lattice
 void neigh_mode_reset(spk_cuda_handle *h) {
   if (!h->kstat || h->neigh_mode != 2) return;
@@ -291,6 +345,19 @@ bool pair_ok(const spk_cuda_handle *h) {
   return h->use_pair && h->tiled && h->use_stream && h->stream_ok && h->d.lattice == SPK_SC_26N && !ising_like(h->d.model);
 }
 
+// one colour class on the 16-bit shadow: 0 launched, -1 not applicable, >0 error
+int shadow16_m(spk_cuda_handle *h, int color, const int32_t *box) {
+  switch (h->d.model) {
+    case SPK_POTTS: return ModelEntry<SPK_POTTS>::shadow16(h, color, box);
+    case SPK_POTTS_PIN: return ModelEntry<SPK_POTTS_PIN>::shadow16(h, color, box);
+    default: return -1;
+  }
+}
+// spk_cuda_sweeps may run on the shadow: eligible handle, tuned kernels allowed, no masks, no colour pairs
+bool shadow_usable(const spk_cuda_handle *h) {
+  return h->shadow_ok && h->tiled && h->use_stream && !h->mask && !h->use_pair;
+}
+
 int sweep_pair_m(spk_cuda_handle *h, int color, const int32_t *box) {
   switch (h->d.model) {
     case SPK_ISING: return ModelEntry<SPK_ISING>::pair(h, color, box);
@@ -316,6 +383,7 @@ int sweep_set(spk_cuda_handle *h, int rng, int color, const int32_t *box, int nl
   if (color < 1 || color > h->nc) return fail("colour %d out of range 1..%d", color, h->nc);
   if (nloop < 1) return fail("nloop must be >= 1");
   CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, true)) return 1;
   if (color == 1 && rng == RNG_PHILOX && neigh_mode_update(h)) return 1;
   switch (h->d.model) {
     case SPK_ISING: return ModelEntry<SPK_ISING>::sweep_set(h, rng, color, box, nloop);
@@ -477,6 +545,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
     if (h->peer_map[side]) cudaIpcCloseMemHandle(h->peer_map[side]);
     if (h->peer_map_alt[side]) cudaIpcCloseMemHandle(h->peer_map_alt[side]);
     if (h->peer_flag_map[side]) cudaIpcCloseMemHandle(h->peer_flag_map[side]);
+    if (h->peer_map16[side]) cudaIpcCloseMemHandle(h->peer_map16[side]);
   }
   cudaFree(h->flags);
   cudaFree(h->edge);
@@ -487,6 +556,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   cudaFree(h->cl_glabel); cudaFree(h->cl_gsize); cudaFree(h->cl_layer); cudaFree(h->cl_pairs); cudaFree(h->cl_flags);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->mask_base);
+  cudaFree(h->shadow_base);
   cudaFree(h->base); cudaFree(h->base_alt); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
   for (cudaEvent_t e : h->laps) cudaEventDestroy(e);
   if (h->t0) cudaEventDestroy(h->t0);
@@ -508,6 +578,8 @@ int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n) {
   CU(cudaSetDevice(h->d.device));
   CU(cudaMemcpyAsync(h->spin, host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   h->ghosts_valid = false;
+  h->canon_current = true;   // every owned site replaced: nothing of the shadow is needed
+  h->shadow_current = false;
   neigh_mode_reset(h);
   // the reference's init_app refuses spins outside 1..Q (Q+1 = pinned for potts/pin); the kernels
   // rely on it (packed 16-bit compares), so the check is repeated where the spins enter the device
@@ -526,6 +598,7 @@ int spk_cuda_download_spins(spk_cuda_handle *h, int32_t *host, int64_t n) {
   if (!h || !host) return fail("null argument");
   if (n != h->nlocal) return fail("download of %lld sites, slab owns %lld", (long long)n, (long long)h->nlocal);
   CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, false)) return 1;
   CU(cudaMemcpyAsync(host, h->spin, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -549,6 +622,7 @@ int spk_cuda_randomize(spk_cuda_handle *h, uint64_t seed, int32_t lo, int32_t hi
     if (lo < 1 || hi > top) return fail("One or more sites have invalid values (range %d..%d outside 1..%d)", lo, hi, top);
   }
   CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, true)) return 1;
   const int64_t goff = (int64_t)h->g.g0 * h->plane;
   randomize_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, goff, seed, lo, (uint32_t)(hi - lo + 1));
   h->ghosts_valid = false;
@@ -565,6 +639,7 @@ int spk_cuda_set_site_range(spk_cuda_handle *h, int32_t park_seed, int32_t lo, i
   const int top = ising_like(h->d.model) ? 2 : h->d.nspins + (h->d.model == SPK_POTTS_PIN ? 1 : 0);
   if (lo < 1 || hi > top) return fail("One or more sites have invalid values (range %d..%d outside 1..%d)", lo, hi, top);
   CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, true)) return 1;
   const long long goff = (long long)h->g.g0 * h->plane;
   set_range_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, goff, (uint32_t)park_seed, lo, hi - lo + 1);
   h->ghosts_valid = false;
@@ -580,6 +655,7 @@ int spk_cuda_site_energy(spk_cuda_handle *h, unsigned char *host, int64_t n) {
   if (!h || !host) return fail("null argument");
   if (n != h->nlocal) return fail("site energies of %lld sites, slab owns %lld", (long long)n, (long long)h->nlocal);
   CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, false)) return 1;
   int rc = spk_cuda_halo_exchange(h);  // site_energy reads the ghosts (src/dump.cpp: comm before the pack)
   if (rc) return rc;
   unsigned char *d = nullptr;
@@ -608,6 +684,7 @@ int spk_cuda_pin_random(spk_cuda_handle *h, uint64_t seed, double fraction) {
   if (h->d.model != SPK_POTTS_PIN) return fail("pin is only defined for app_style potts/pin");
   if (fraction < 0.0 || fraction > 1.0) return fail("Illegal pin command");
   CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, true)) return 1;
   const int64_t goff = (int64_t)h->g.g0 * h->plane;
   double t = std::floor(fraction * 4294967296.0);
   const uint32_t thr = t > 4294967295.0 ? 4294967295u : (uint32_t)t;
@@ -672,6 +749,7 @@ static int check_halo_timeout(spk_cuda_handle *h);
 
 int spk_cuda_halo_exchange(spk_cuda_handle *h) {
   if (!h) return fail("null handle");
+  if (h->d.nranks > 1 && use_canon(h, true)) return 1;  // the exchange rewrites the int32 ghost planes
   const int rc = halo_exchange_on(h, h->stream);
   if (rc == 0) h->ghosts_valid = true;
   return rc;
@@ -766,17 +844,29 @@ static int sweeps_overlapped(spk_cuda_handle *h, uint32_t first_sweep, int nswee
 // (WAR; within one step the planes a colour updates and the ghost planes it reads have opposite
 // parity, so same-step launches never touch the same words).
 static int sweeps_p2p(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
+  const bool on16 = shadow_usable(h) && h->mirror16_lo && h->mirror16_hi;
   if (!h->ghosts_valid) {  // spins changed outside spk_cuda_sweeps: one NCCL exchange re-seeds the ghosts
+    if (use_canon(h, true)) return 1;
     int rc = halo_exchange_on(h, h->stream);
     if (rc) return rc;
   }
+  if (on16) {  // boundary launches store into the neighbours' SHADOW ghost planes
+    if (ensure_shadow(h)) return 1;
+    h->canon_current = false;
+  } else if (use_canon(h, true)) return 1;
   const int32_t lo_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0, h->g.g0 + 1};
   const int32_t hi_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0 + h->nslab - 1, h->g.g0 + h->nslab};
   const int32_t in_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0 + 1, h->g.g0 + h->nslab - 1};
   int rc = 0;
   // sc/26n: a step is a colour PAIR (same z parity, so the same-step argument above holds unchanged)
-  const bool pair = pair_ok(h);
-  auto run = [&](int color, const int32_t *box) { return pair ? sweep_pair(h, color, box) : sweep_set(h, RNG_PHILOX, color, box, 1); };
+  const bool pair = !on16 && pair_ok(h);
+  auto run = [&](int color, const int32_t *box) -> int {
+    if (on16) {
+      const int rc = shadow16_m(h, color, box);
+      return rc ? fail("16-bit streaming kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+    }
+    return pair ? sweep_pair(h, color, box) : sweep_set(h, RNG_PHILOX, color, box, 1);
+  };
   for (int s = 0; s < nsweeps && !rc; s++) {
     h->ev.sweep = first_sweep + (uint32_t)s;
     for (int color = 1; color <= h->nc && !rc; color += pair ? 2 : 1) {
@@ -859,6 +949,20 @@ int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
     if (h->dim == 2 && h->use_fused && h->fused2d_ok && !getenv("SPK_CUDA_OVERLAP_2D"))
       return sweeps_p2p_2d(h, first_sweep, nsweeps);
   }
+  if (h->d.nranks == 1 && shadow_usable(h) && nsweeps > 0) {
+    // sc/26n potts / potts/pin on one GPU: every colour launch on the 16-bit shadow (half the DRAM
+    // bytes); the int32 lattice is brought up to date by the next call that needs it
+    if (ensure_shadow(h)) return 1;
+    h->canon_current = false;
+    for (int s = 0; s < nsweeps; s++) {
+      h->ev.sweep = first_sweep + (uint32_t)s;
+      for (int color = 1; color <= h->nc; color++) {
+        const int rc = shadow16_m(h, color, nullptr);
+        if (rc) return fail("16-bit streaming kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      }
+    }
+    return 0;
+  }
   const bool fused2d = h->tiled && h->use_fused && h->dim == 2 && h->fused2d_ok;
   // 3-D: 8 (2) exchanges per sweep, worth hiding.  2-D: one exchange of 4 rows per fused sweep; splitting
   // the single launch into boundary + interior launches costs more than the exchange it hides
@@ -937,6 +1041,7 @@ int spk_cuda_mask_enable(spk_cuda_handle *h, int on) {
   if (!on) {
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(h->mask_base);
+  cudaFree(h->shadow_base);
     h->mask_base = h->mask = nullptr;
     return 0;
   }
@@ -985,6 +1090,7 @@ int spk_cuda_download_mask(spk_cuda_handle *h, unsigned char *host, int64_t n) {
 int spk_cuda_digest(spk_cuda_handle *h, uint64_t *digest) {
   if (!h || !digest) return fail("null argument");
   CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, false)) return 1;
   CU(cudaMemsetAsync(h->escratch, 0, sizeof(unsigned long long), h->stream));
   digest_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, (long long)h->g.g0 * h->plane, h->escratch);
   h->launches++;
@@ -1020,6 +1126,7 @@ static int p2p_read_fence(spk_cuda_handle *h) {
 int spk_cuda_energy(spk_cuda_handle *h, double *energy) {
   if (!h || !energy) return fail("null argument");
   CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, false)) return 1;
   int rc = spk_cuda_halo_exchange(h);  // DiagEnergy::compute calls comm->all() first (src/diag_energy.cpp:56)
   if (rc) return rc;
   CU(cudaMemsetAsync(h->escratch, 0, sizeof(unsigned long long), h->stream));
@@ -1037,7 +1144,7 @@ int spk_cuda_energy(spk_cuda_handle *h, double *energy) {
 // the peer-memory halo.  The handles travel through one ncclAllGather; a second one makes every
 // rank agree on whether the mapping worked everywhere (otherwise all keep the NCCL exchange).
 static int setup_p2p(spk_cuda_handle *h) {
-  struct Ipc { cudaIpcMemHandle_t base, alt, flags; int ok; int pad[3]; };
+  struct Ipc { cudaIpcMemHandle_t base, alt, flags, shadow; int ok, ok16; int pad[2]; };
   h->p2p = false;
   const char *np = getenv("SPK_CUDA_NO_P2P");
   const bool two = h->dim == 2;  // 2-D: both buffers of the out-of-place fused sweep
@@ -1055,6 +1162,8 @@ static int setup_p2p(spk_cuda_handle *h) {
     mine.ok = cudaIpcGetMemHandle(&mine.base, first) == cudaSuccess &&
               (!two || cudaIpcGetMemHandle(&mine.alt, second) == cudaSuccess) &&
               cudaIpcGetMemHandle(&mine.flags, h->flags) == cudaSuccess;
+    // 16-bit shadow (3-D): its ghost planes are written by the neighbours too; all ranks or none
+    mine.ok16 = mine.ok && h->shadow_ok && cudaIpcGetMemHandle(&mine.shadow, h->shadow_base) == cudaSuccess;
     cudaGetLastError();
   }
   Ipc *dev = nullptr;
@@ -1068,8 +1177,9 @@ static int setup_p2p(spk_cuda_handle *h) {
     return 0;
   };
   int rc = gather();
-  bool every = rc == 0;
+  bool every = rc == 0, every16 = rc == 0;
   for (int r = 0; r < n && every; r++) every = all[r].ok != 0;
+  for (int r = 0; r < n && every16; r++) every16 = all[r].ok16 != 0;
   if (every) {  // open the neighbours' allocations (one mapping when both neighbours are the same rank)
     const int peers[2] = {lower, upper};
     for (int side = 0; side < 2 && mine.ok; side++) {
@@ -1077,9 +1187,14 @@ static int setup_p2p(spk_cuda_handle *h) {
         h->peer_map[1] = h->peer_map[0];
         h->peer_map_alt[1] = h->peer_map_alt[0];
         h->peer_flag_map[1] = h->peer_flag_map[0];
+        h->peer_map16[1] = h->peer_map16[0];
         continue;
       }
       const Ipc &p = all[peers[side]];
+      if (every16 && cudaIpcOpenMemHandle(&h->peer_map16[side], p.shadow, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        mine.ok16 = 0;
+      }
       if (cudaIpcOpenMemHandle(&h->peer_map[side], p.base, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
           (two && cudaIpcOpenMemHandle(&h->peer_map_alt[side], p.alt, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ||
           cudaIpcOpenMemHandle(&h->peer_flag_map[side], p.flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
@@ -1090,6 +1205,7 @@ static int setup_p2p(spk_cuda_handle *h) {
     rc = gather();  // agreement round
     every = rc == 0;
     for (int r = 0; r < n && every; r++) every = all[r].ok != 0;
+    for (int r = 0; r < n && every16; r++) every16 = all[r].ok16 != 0;
   }
   cudaFree(dev);
   if (rc) return rc;
@@ -1100,7 +1216,13 @@ static int setup_p2p(spk_cuda_handle *h) {
     h->peer_flags[0] = (uint32_t *)h->peer_flag_map[0] + 1;  // I am the lower neighbour's upper neighbour
     h->peer_flags[1] = (uint32_t *)h->peer_flag_map[1] + 0;
     h->p2p = true;
+    if (every16) {  // the shadow's ghost planes: plane 0 (lower) and plane nslab+1 (upper) of its allocation
+      h->mirror16_lo = (uint16_t *)h->peer_map16[0] + (int64_t)(1 + h->nslab) * h->plane;
+      h->mirror16_hi = (uint16_t *)h->peer_map16[1];
+    }
   }
+  // without peer memory (or without every rank's shadow) a multi-rank run keeps the int32 lattice
+  if (!(every && every16)) h->shadow_ok = false;
   return 0;
 }
 
@@ -1145,6 +1267,7 @@ static int cluster_across_slabs(spk_cuda_handle *h, unsigned long long *ncluster
 static int cluster_analyse(spk_cuda_handle *h, unsigned long long *ncluster, double *rsum) {
   if (h->nlocal >= (int64_t)1 << 32) return fail("cluster analysis needs fewer than 2^32 sites per GPU");
   CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, false)) return 1;
   const long long n = h->nlocal;
   const bool multi = h->d.nranks > 1;
   if (multi) {
@@ -1382,6 +1505,8 @@ int spk_cuda_launch_count(spk_cuda_handle *h, int64_t *launches) {
 
 int spk_cuda_device_spins(spk_cuda_handle *h, void **dptr) {
   if (!h || !dptr) return fail("null argument");
+  CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, true)) return 1;
   *dptr = h->spin;
   h->ghosts_valid = false;  // the caller may write through the pointer: re-seed the ghosts at the next sweep
   return 0;

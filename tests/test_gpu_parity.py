@@ -199,6 +199,8 @@ def _kernel_cases():
             out.append(c + (kernel,))
         if c[0] in ("potts/neighonly", "potts/neigh") and c[1] == "sc/26n":
             out.append(c + ("adaptive",))  # candidate elimination instead of the all-pairs chain
+        if c[0] in ("potts", "potts/pin") and c[1] == "sc/26n":
+            out.append(c + ("int32stream",))  # "tuned" sweeps on the 16-bit shadow where it applies: keep the int32 kernel covered
     return out
 
 
@@ -210,6 +212,8 @@ def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, kernel, monkeypa
     evaluating the same counter-based stream."""
     if kernel == "adaptive":
         monkeypatch.setenv("SPK_CUDA_NEIGH_MODE", "adaptive")
+    if kernel == "int32stream":
+        monkeypatch.setenv("SPK_CUDA_NO_SHADOW16", "1")
     if kernel == "tuned":
         monkeypatch.setenv("SPK_CUDA_NEIGH_MODE", "chain")
     if kernel == "generic":
@@ -289,6 +293,44 @@ def test_candidate_elimination_vs_oracle(model, mode, start, monkeypatch):
     assert s.counters() == (nacc, nsweeps * o.nsites)
     if mode == "auto":
         assert s.neigh_variant() in ("chain", "adaptive")
+
+
+@pytest.mark.parametrize("model", ["potts", "potts/pin"])
+def test_shadow16_interleaved_with_int32_calls(model):
+    """sc/26n potts / potts/pin: spk_cuda_sweeps runs on the 16-bit shadow of the lattice; every other
+    entry point works on the int32 lattice.  Interleave them (sweeps, per-colour calls, energy, pin,
+    download, upload, randomize) and compare with the oracle after every step: the lazy conversions
+    must never lose an update.  Several x / y tiles, ragged edges, Q near the 16-bit limit."""
+    rng = np.random.default_rng(3)
+    n, q, T, seed = (520, 70, 12), 65000, 0.6, 2468
+    o = O.Oracle(model, "sc/26n", n[0], n[1], n[2], q, T)
+    spins = rng.integers(1, q + 1, size=o.nsites, dtype=np.int32)
+    if model == "potts/pin":
+        spins[rng.random(o.nsites) < 0.03] = q + 1
+    s = _sweep(model, "sc/26n", n, q, T, seed=seed)
+    s.upload(spins)
+    want = spins.copy()
+    sw = 0
+    s.sweeps(sw, 2)                                   # shadow
+    for _ in range(2):
+        o.sweep_philox(want, seed, sw); sw += 1
+    assert s.energy() == o.total_energy(want)        # int32 (converted back)
+    s.sweeps(sw, 1)                                   # shadow again (still current: no re-pack needed)
+    o.sweep_philox(want, seed, sw); sw += 1
+    for c in range(1, 9):                             # per-colour calls on the int32 lattice
+        s.sweep_color(sw, c)
+        o.halfsweep_philox(want, seed, sw, c)
+    sw += 1
+    s.sweeps(sw, 1)                                   # shadow must be re-packed
+    o.sweep_philox(want, seed, sw); sw += 1
+    assert np.array_equal(s.download(), want)
+    want2 = np.roll(want, 7)
+    s.upload(want2)                                   # replaces both copies
+    s.sweeps(sw, 2)
+    for _ in range(2):
+        o.sweep_philox(want2, seed, sw); sw += 1
+    assert s.digest() is not None and np.array_equal(s.download(), want2)
+    assert s.energy() == o.total_energy(want2)
 
 
 def test_per_colour_calls_equal_fused_sweeps():
