@@ -84,6 +84,10 @@ struct spk_cuda_handle {
   bool shadow_current = false;  // holds the current spins (incl. ghost planes when ghosts_valid)
   bool canon_current = true;    // the int32 lattice holds the current spins
   bool smem16_set = false;
+  // bit shadow of a two-state 2-D lattice (sweep_bits2d.cuh): ising / ising/single on sq/4n, one GPU;
+  // shares shadow_current / canon_current with the 16-bit shadow (a handle has at most one of them)
+  uint32_t *bits = nullptr;
+  bool bits_ok = false;
   void *peer_map16[2] = {nullptr, nullptr};            // the ring neighbours' shadow allocations (peer memory)
   uint16_t *mirror16_lo = nullptr, *mirror16_hi = nullptr;
   int32_t *base_alt = nullptr;  // second lattice buffer of the out-of-place fused 2-D sweep

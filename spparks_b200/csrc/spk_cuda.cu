@@ -18,6 +18,7 @@
 #include "cluster.cuh"
 #include "sweep_stream.cuh"   // StreamCfg (tensor-map box shapes)
 #include "sweep_stream16.cuh" // Stream16Cfg, shadow conversion kernels
+#include "sweep_bits2d.cuh"   // multi-spin-coded ising kernel and its conversion kernels
 #include "sweep_tile2d.cuh"   // Tile2dCfg
 
 namespace {
@@ -232,6 +233,13 @@ int build_tensor_map(spk_cuda_handle *h) {
 // stale; conversions cover the ghost planes too, so `ghosts_valid` speaks for both
 int ensure_canon(spk_cuda_handle *h) {
   if (h->canon_current) return 0;
+  if (h->bits_ok) {
+    bits2d_unpack_kernel<<<148 * 8, 256, 0, h->stream>>>(h->bits, h->spin, h->g.Y, h->g.X / 64);
+    h->launches++;
+    CU(cudaGetLastError());
+    h->canon_current = true;
+    return 0;
+  }
   const long long n8 = (h->nlocal + 2 * h->plane) / 8;
   shadow_unpack_kernel<<<148 * 8, 256, 0, h->stream>>>(reinterpret_cast<const uint4 *>(h->shadow_base),
                                                        reinterpret_cast<int4 *>(h->base), n8);
@@ -242,6 +250,13 @@ int ensure_canon(spk_cuda_handle *h) {
 }
 int ensure_shadow(spk_cuda_handle *h) {
   if (h->shadow_current) return 0;
+  if (h->bits_ok) {
+    bits2d_pack_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->bits, h->g.Y, h->g.X / 64);
+    h->launches++;
+    CU(cudaGetLastError());
+    h->shadow_current = true;
+    return 0;
+  }
   const long long n8 = (h->nlocal + 2 * h->plane) / 8;
   shadow_pack_kernel<<<148 * 8, 256, 0, h->stream>>>(reinterpret_cast<const int4 *>(h->base),
                                                      reinterpret_cast<uint4 *>(h->shadow_base), n8);
@@ -511,6 +526,14 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
     }
   }
   build_tensor_map(h);
+  {  // bit shadow: two-state app on sq/4n, rows of whole 64-cell groups, one GPU
+    const char *nb = getenv("SPK_CUDA_NO_BITS");
+    if (ising_like(desc->model) && desc->lattice == SPK_SQ_4N && desc->nranks == 1 && desc->nx % 64 == 0 && h->tiled &&
+        h->use_fused && !(nb && nb[0] == '1')) {
+      if (cudaMalloc(&h->bits, (size_t)h->nlocal / 8) == cudaSuccess) h->bits_ok = true;
+      else cudaGetLastError();
+    }
+  }
   if (h->tmap8_ok) {
     const char *nm = getenv("SPK_CUDA_NEIGH_MODE");
     h->neigh_mode = !nm ? 2 : !strcmp(nm, "chain") ? 0 : !strcmp(nm, "adaptive") ? 1 : 2;
@@ -557,6 +580,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->mask_base);
   cudaFree(h->shadow_base);
+  cudaFree(h->bits);
   cudaFree(h->base); cudaFree(h->base_alt); cudaFree(h->u1); cudaFree(h->u2); cudaFree(h->seeds); cudaFree(h->naccept);
   for (cudaEvent_t e : h->laps) cudaEventDestroy(e);
   if (h->t0) cudaEventDestroy(h->t0);
@@ -949,6 +973,28 @@ int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
     if (h->dim == 2 && h->use_fused && h->fused2d_ok && !getenv("SPK_CUDA_OVERLAP_2D"))
       return sweeps_p2p_2d(h, first_sweep, nsweeps);
   }
+  if (h->bits_ok && !h->mask && nsweeps > 0) {
+    // ising / ising/single on sq/4n, one GPU: multi-spin-coded colour kernels on the bit shadow
+    if (ensure_shadow(h)) return 1;
+    h->canon_current = false;
+    Bits2dArgs ba;
+    ba.bits = h->bits; ba.Y = h->g.Y; ba.W = h->g.X / 64; ba.gX = (unsigned long long)h->g.gX; ba.naccept = h->naccept;
+    const long long nwords = (long long)ba.W * ba.Y;
+    const int grid = (int)std::min<long long>(148 * 16, (nwords + 127) / 128);
+    for (int s = 0; s < nsweeps; s++) {
+      h->ev.sweep = first_sweep + (uint32_t)s;
+      ba.ev = h->ev;
+      for (int c0 = 0; c0 < 2; c0++) {
+        ba.c0 = c0;
+        if (h->d.model == SPK_ISING) sweep_bits2d_kernel<SPK_ISING><<<grid, 128, 0, h->stream>>>(ba);
+        else sweep_bits2d_kernel<SPK_ISING_SINGLE><<<grid, 128, 0, h->stream>>>(ba);
+      }
+      h->launches += 2;
+      h->nattempt += h->nlocal;
+    }
+    CU(cudaGetLastError());
+    return 0;
+  }
   if (h->d.nranks == 1 && shadow_usable(h) && nsweeps > 0) {
     // sc/26n potts / potts/pin on one GPU: every colour launch on the 16-bit shadow (half the DRAM
     // bytes); the int32 lattice is brought up to date by the next call that needs it
@@ -1042,6 +1088,7 @@ int spk_cuda_mask_enable(spk_cuda_handle *h, int on) {
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(h->mask_base);
   cudaFree(h->shadow_base);
+  cudaFree(h->bits);
     h->mask_base = h->mask = nullptr;
     return 0;
   }

@@ -136,6 +136,9 @@ def test_strict_runs_bit_exact_vs_reference(path):
 CASES = [
     ("ising", "sq/4n", (64, 48, 1), 2, 1.1346),
     ("ising", "sq/4n", (50, 50, 1), 2, 0.0),
+    ("ising", "sq/4n", (128, 66, 1), 2, 0.0),       # T = 0 on the bit shadow (thresholds unused)
+    ("ising", "sq/4n", (192, 40, 1), 2, 7.0),       # hot: most uphill moves accepted
+    ("ising/single", "sq/4n", (256, 36, 1), 2, 0.8),
     ("ising", "sc/6n", (16, 12, 10), 2, 2.25),
     ("potts", "sq/8n", (34, 22, 1), 7, 0.6),
     ("potts", "tri", (30, 17, 1), 9, 0.5),
@@ -199,6 +202,8 @@ def _kernel_cases():
             out.append(c + (kernel,))
         if c[0] in ("potts/neighonly", "potts/neigh") and c[1] == "sc/26n":
             out.append(c + ("adaptive",))  # candidate elimination instead of the all-pairs chain
+        if c[0] in ("ising", "ising/single") and c[1] == "sq/4n" and c[2][0] % 64 == 0:
+            out.append(c + ("nobits",))  # "tuned" runs on the bit shadow there: keep the colour-fused int32 kernel covered
         if c[0] in ("potts", "potts/pin") and c[1] == "sc/26n":
             out.append(c + ("int32stream",))  # "tuned" sweeps on the 16-bit shadow where it applies: keep the int32 kernel covered
     return out
@@ -212,6 +217,8 @@ def test_philox_sweeps_bit_exact_vs_oracle(model, lat, n, q, T, kernel, monkeypa
     evaluating the same counter-based stream."""
     if kernel == "adaptive":
         monkeypatch.setenv("SPK_CUDA_NEIGH_MODE", "adaptive")
+    if kernel == "nobits":
+        monkeypatch.setenv("SPK_CUDA_NO_BITS", "1")
     if kernel == "int32stream":
         monkeypatch.setenv("SPK_CUDA_NO_SHADOW16", "1")
     if kernel == "tuned":
@@ -293,6 +300,40 @@ def test_candidate_elimination_vs_oracle(model, mode, start, monkeypatch):
     assert s.counters() == (nacc, nsweeps * o.nsites)
     if mode == "auto":
         assert s.neigh_variant() in ("chain", "adaptive")
+
+
+@pytest.mark.parametrize("model", ["ising", "ising/single"])
+def test_bit_shadow_interleaved_with_int32_calls(model):
+    """ising / ising/single on sq/4n: spk_cuda_sweeps runs multi-spin coded on a bit copy of the
+    lattice; interleaved with calls that work on the int32 lattice (per-colour sweeps, energy, download,
+    upload, randomize) nothing may be lost in the lazy conversions."""
+    rng = np.random.default_rng(8)
+    n, T, seed = (320, 46, 1), 1.2, 97531
+    o = O.Oracle(model, "sq/4n", n[0], n[1], 1, 2, T)
+    spins = rng.integers(1, 3, size=o.nsites, dtype=np.int32)
+    s = _sweep(model, "sq/4n", n, 2, T, seed=seed)
+    s.upload(spins)
+    want = spins.copy()
+    sw = 0
+    s.sweeps(sw, 3)
+    nacc = 0
+    for _ in range(3):
+        nacc += o.sweep_philox(want, seed, sw); sw += 1
+    assert s.counters() == (nacc, 3 * o.nsites)
+    assert s.energy() == o.total_energy(want)
+    for c in (1, 2):
+        s.sweep_color(sw, c)
+        o.halfsweep_philox(want, seed, sw, c)
+    sw += 1
+    s.sweeps(sw, 2)
+    for _ in range(2):
+        o.sweep_philox(want, seed, sw); sw += 1
+    assert np.array_equal(s.download(), want)
+    s.randomize(5, 1, 2)
+    got0 = s.download()
+    s.sweeps(sw, 1)
+    o.sweep_philox(got0, seed, sw)
+    assert np.array_equal(s.download(), got0)
 
 
 @pytest.mark.parametrize("model", ["potts", "potts/pin"])
