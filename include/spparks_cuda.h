@@ -133,6 +133,13 @@ int spk_cuda_sweeps(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps);
 int spk_cuda_counters(spk_cuda_handle *h, int64_t *naccept, int64_t *nattempt);
 int spk_cuda_reset_counters(spk_cuda_handle *h);
 
+/* Which colour kernel spk_cuda_sweeps launches for this handle, how many launches of it make one
+ * sweep, and the width of the lattice copy it sweeps on (4 = the int32 lattice, 2 = the 16-bit
+ * shadow of sc/26n potts / potts/pin, 0 = the 1-bit shadow of ising on sq/4n; the narrower copies
+ * are converted from / to the int32 lattice lazily at the boundaries of spk_cuda_sweeps).
+ * bench.py reports it next to the roofline so that narrower device types are visible. */
+int spk_cuda_sweep_path(spk_cuda_handle *h, char *name, int capacity, int *launches_per_sweep, int *bytes_per_spin);
+
 /* Candidate-list apps (potts/neighonly, potts/neigh) on sc/26n: which of the two equivalent
  * first-occurrence algorithms (src/app_potts_neighonly.cpp:81-88) the colour kernels currently use:
  * 0 = all-pairs chain (cost independent of the spins), 1 = candidate elimination (cost

@@ -27,6 +27,7 @@ SYMBOLS = [
     "spk_cuda_cluster_ids", "spk_cuda_neigh_variant", "spk_cuda_timer_lap", "spk_cuda_timer_laps",
     "spk_cuda_digest", "spk_cuda_mask_enable", "spk_cuda_mask_clear_border", "spk_cuda_download_mask",
     "spk_cuda_host_register", "spk_cuda_host_unregister", "spk_cuda_set_site_range", "spk_cuda_site_energy",
+    "spk_cuda_sweep_path",
 ]
 
 
@@ -93,6 +94,7 @@ def load():
     L.spk_cuda_host_unregister.argtypes = [vp]
     L.spk_cuda_set_site_range.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.spk_cuda_site_energy.argtypes = [vp, vp, C.c_int64]
+    L.spk_cuda_sweep_path.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.spk_cuda_digest.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.spk_cuda_timer_lap.argtypes = [vp]
     L.spk_cuda_timer_laps.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]

@@ -1,6 +1,7 @@
 // Per-site rejection event (site_event_rejection of the four apps) and the random sources.
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 #include "dedupe_chain.cuh"
 #include "lattice.cuh"
 
@@ -350,9 +351,13 @@ __device__ __forceinline__ int site_event_nb26(const EventParams &p, int old, co
 // einitial (optional, `sweep ... mask yes`): receives the initial energy when the event ran to its
 // end, -1 when it returned early (pinned site, no candidate, null bin): the reference's mask
 // update sits after those returns (src/app_potts_neighonly.cpp:90, 107-117).
-template <int MODEL, int RNG, int NN, bool P16 = false>
+// fetch (optional, candidate-list apps): fetch(n) returns v[n] for a run-time slot n from wherever the
+// caller keeps the neighbourhood addressable (the streaming kernel: its shared-memory planes); without
+// it the value is picked out of the registers by a select tree (~20 ALU instructions per site).
+struct NoFetch {};
+template <int MODEL, int RNG, int NN, bool P16 = false, class Fetch = NoFetch>
 __device__ __forceinline__ int site_event(const EventParams &p, int old, const int (&v)[NN], Draws<RNG> &d,
-                                          int *kstat = nullptr, int *einitial = nullptr) {
+                                          int *kstat = nullptr, int *einitial = nullptr, Fetch fetch = Fetch()) {
   const int Q = p.nspins;
   if (einitial) *einitial = -1;
   if (MODEL == SPK_POTTS_PIN && old > Q) return old;  // pinned: no draw (src/app_potts_pin.cpp:97)
@@ -400,7 +405,8 @@ __device__ __forceinline__ int site_event(const EventParams &p, int old, const i
     if constexpr (NULLBIN) {
       if (pick >= nevent) return old;
     }
-    if constexpr (PK) trial = select_slot16<NN>(negp, nth_set_bit(first, pick));
+    if constexpr (!std::is_same<Fetch, NoFetch>::value) trial = fetch(nth_set_bit(first, pick));
+    else if constexpr (PK) trial = select_slot16<NN>(negp, nth_set_bit(first, pick));
     else trial = select_slot<NN>(v, nth_set_bit(first, pick));
   } else if constexpr (MODEL == SPK_ISING_SINGLE) {
     trial = 3 - old;  // spins are 1 or 2 (src/app_ising_single.cpp:46-47)

@@ -1148,6 +1148,23 @@ int spk_cuda_digest(spk_cuda_handle *h, uint64_t *digest) {
   return 0;
 }
 
+int spk_cuda_sweep_path(spk_cuda_handle *h, char *name, int capacity, int *launches_per_sweep, int *bytes_per_spin) {
+  if (!h || !name || capacity < 1) return fail("null argument");
+  const char *k;
+  int per = h->nc, width = 4;
+  const bool multi = h->d.nranks > 1;
+  if (h->mask || !h->tiled) k = "sweep_generic_kernel";
+  else if (h->bits_ok) { k = "sweep_bits2d_kernel"; per = 2; width = 0; }
+  else if (shadow_usable(h) && (!multi || (h->p2p && h->mirror16_lo))) { k = "sweep_stream16_kernel"; width = 2; }
+  else if (h->dim == 2 && h->use_fused && h->fused2d_ok) { k = "sweep_tile2d_kernel"; per = 1; }
+  else if (h->dim == 3 && h->use_stream && h->stream_ok) k = "sweep_stream_kernel";
+  else k = "sweep_strip_kernel / sweep_generic_kernel";
+  snprintf(name, (size_t)capacity, "%s", k);
+  if (launches_per_sweep) *launches_per_sweep = per;
+  if (bytes_per_spin) *bytes_per_spin = width;  // 0 = one bit
+  return 0;
+}
+
 int spk_cuda_neigh_variant(spk_cuda_handle *h, int *variant, double *mean_distinct) {
   if (!h || !variant) return fail("null argument");
   *variant = h->tmap8_ok && h->tiled && h->use_stream ? (h->neigh_adaptive ? 1 : 0) : -1;

@@ -129,10 +129,12 @@ __device__ __forceinline__ void patch_store(const PatchPlan &pp, int32_t *pl, in
 }
 
 // one class row of one class plane: the thread's 16-byte chunk holds two class sites at P, P+2
+// nbtab (candidate-list apps on sc/26n): byte offset of neighbour slot n relative to the site itself
+// inside the shared-memory planes of this step, for the run-time fetch of the chosen candidate
 template <int LAT, int MODEL, int P, bool ONEPASS, bool P16>
 __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *const (&pl)[3], int r, int lane,
                                             int32_t *gchunk, int32_t *gmirror, unsigned long long gsite0, int xcell,
-                                            int *kstat = nullptr) {
+                                            int *kstat = nullptr, const int *nbtab = nullptr) {
   using L = Lat<LAT>;
   constexpr int NN = L::NN;
   using R = RowInfo<LAT, 0>;
@@ -177,7 +179,19 @@ __device__ __forceinline__ int stream_chunk(const SweepArgs &a, const int32_t *c
         d.w1 = h ? blk.z : blk.x;
         d.w2 = h ? blk.w : blk.y;
       }
-      const int nw = site_event<MODEL, RNG_PHILOX, NN, P16>(a.ev, cur[h], v, d, kstat);
+      int nw;
+      if constexpr (LAT == SPK_SC_26N && neigh_like(MODEL)) {
+        const uint32_t self = smem_u32(pl[1] + r * ST_BX + 4 + 4 * lane + e), tab = smem_u32(nbtab);
+        auto fetch = [&](int n) {
+          int off, val;
+          asm("ld.shared.s32 %0, [%1];" : "=r"(off) : "r"(tab + 4u * (uint32_t)n));
+          asm("ld.shared.s32 %0, [%1];" : "=r"(val) : "r"(self + (uint32_t)off));
+          return val;
+        };
+        nw = site_event<MODEL, RNG_PHILOX, NN, P16>(a.ev, cur[h], v, d, kstat, nullptr, fetch);
+      } else {
+        nw = site_event<MODEL, RNG_PHILOX, NN, P16>(a.ev, cur[h], v, d, kstat);
+      }
       accepted += (nw != cur[h]);
       cur[h] = nw;
     });
@@ -401,14 +415,15 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     for (int i = 0; i < C::RING; i++) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if constexpr (ADAPT) {
-    // nbtabs[c][b]: the window's middle plane sits in ring slot (c + 1) % RING; bit b -> slot ->
-    // (dx,dy,dz) in reference order (lattice.cuh) -> byte offset from the site's own element
+  if constexpr (LAT == SPK_SC_26N && neigh_like(MODEL) && !PAIR) {
+    // nbtabs[c][b]: the window's middle plane sits in ring slot (c + 1) % RING; entry b = mask bit b
+    // (candidate elimination) or neighbour slot b (all-pairs chain) -> (dx,dy,dz) in reference
+    // order (lattice.cuh) -> byte offset from the site's own element
     if (tid < C::RING * 32) {
       const int c = tid >> 5, b = tid & 31;
       int off = 0;
-      if ((NB26_VALID >> b) & 1) {
-        const Off o = Lat<SPK_SC_26N>::off(0, nb26_bit_to_slot(b));
+      if (ADAPT ? ((NB26_VALID >> b) & 1) != 0 : b < 26) {
+        const Off o = Lat<SPK_SC_26N>::off(0, ADAPT ? nb26_bit_to_slot(b) : b);
         const int mid = (c + 1) % C::RING, pln = (c + 1 + o.dz + C::RING) % C::RING;
         off = (pln - mid) * C::PLANE_STRIDE + (o.dy * ST_BX + o.dx) * 4;
       }
@@ -534,8 +549,8 @@ sweep_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             if (px) accepted += stream_chunk_nb26<MODEL, 1, ONEPASS>(a, pl, r, lane, gchunk, gmirror, gsite0, nbtab, &kstat);
             else accepted += stream_chunk_nb26<MODEL, 0, ONEPASS>(a, pl, r, lane, gchunk, gmirror, gsite0, nbtab, &kstat);
           } else {
-            if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x, &kstat);
-            else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x, &kstat);
+            if (px) accepted += stream_chunk<LAT, MODEL, 1, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x, &kstat, nbtab);
+            else accepted += stream_chunk<LAT, MODEL, 0, ONEPASS, P16>(a, pl, r, lane, gchunk, gmirror, gsite0, x, &kstat, nbtab);
           }
         }
         gptr[t] += C::KSTEP * sz;

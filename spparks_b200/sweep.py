@@ -170,6 +170,13 @@ class LatticeSweep:
         _lib.check(self.L.spk_cuda_download_mask(self.h, out.ctypes.data_as(C.c_void_p), self.nlocal))
         return out
 
+    def sweep_path(self):
+        """(kernel name, launches per sweep, bytes per spin of the copy it sweeps on; 0 = one bit)."""
+        buf = C.create_string_buffer(128)
+        per, width = C.c_int(), C.c_int()
+        _lib.check(self.L.spk_cuda_sweep_path(self.h, buf, 128, C.byref(per), C.byref(width)))
+        return buf.value.decode(), per.value, width.value
+
     def digest(self):
         """Order-independent 64-bit digest of the owned spins (global site index, value)."""
         d = C.c_uint64()
