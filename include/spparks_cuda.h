@@ -178,6 +178,8 @@ int spk_cuda_cluster_ids(spk_cuda_handle *h, int32_t *ids, int64_t *volumes, int
  * ghost layers stale, and spk_cuda_sweeps re-seeds them with one exchange in which all ranks take
  * part; and the calls that read the ghost layers (energy, site_energy, cluster_stats), which end
  * with a handshake so that no neighbour's next sweep can overtake a slower rank's read.
+ * spk_cuda_destroy of a handle that took part in spk_cuda_comm_init is collective too: nobody
+ * frees lattice memory that a neighbour still has mapped.
  *
  * multi-GPU: one process per GPU; rank 0 creates the id, the host broadcasts it (MPI_Bcast in
  * the plugin, torch.distributed in bench.py), every rank joins.  Replaces CommLattice::init

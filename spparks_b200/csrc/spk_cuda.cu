@@ -570,6 +570,17 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
     if (h->peer_flag_map[side]) cudaIpcCloseMemHandle(h->peer_flag_map[side]);
     if (h->peer_map16[side]) cudaIpcCloseMemHandle(h->peer_map16[side]);
   }
+  // Peer memory: an exported allocation must not be freed while a neighbour still has it mapped
+  // (cudaIpcGetMemHandle: "calling cudaFree on an exported memory region before calling
+  // cudaIpcCloseMemHandle in the importing context will result in undefined behavior" — seen as
+  // wrong spins in LATER handles of the same processes at 8 GPUs).  Every rank has closed its
+  // mappings above; one all-reduce makes sure of it before anybody frees.  Destroy of a
+  // multi-rank handle is therefore collective, like its create + comm_init.
+  if (h->p2p && h->comm && g_nccl.AllReduce && h->flags) {
+    if (g_nccl.AllReduce(h->flags + 3, h->flags + 3, 1, ncclInt32, ncclMax, h->comm, h->stream) == ncclSuccess)
+      cudaStreamSynchronize(h->stream);
+    cudaGetLastError();
+  }
   cudaFree(h->flags);
   cudaFree(h->edge);
   cudaFree(h->kstat);
@@ -877,6 +888,11 @@ static int sweeps_p2p(spk_cuda_handle *h, uint32_t first_sweep, int nsweeps) {
   if (on16) {  // boundary launches store into the neighbours' SHADOW ghost planes
     if (ensure_shadow(h)) return 1;
     h->canon_current = false;
+    // the conversion above rewrites this rank's whole shadow, ghost planes included: no neighbour
+    // may store its first boundary step into them before it has finished (seen at 8 GPUs as wrong
+    // spins: a faster neighbour's mirrored plane overwritten by the slower rank's pack).  One
+    // signal / wait step, on every call (a rank cannot know whether its neighbours had to convert).
+    if (p2p_read_fence(h)) return 1;
   } else if (use_canon(h, true)) return 1;
   const int32_t lo_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0, h->g.g0 + 1};
   const int32_t hi_box[6] = {0, h->g.gX, 0, h->g.gY, h->g.g0 + h->nslab - 1, h->g.g0 + h->nslab};

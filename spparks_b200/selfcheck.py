@@ -68,8 +68,12 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
             mine = torch.from_numpy(s.download()).cuda()
             parts = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(parts, mine)
-            acc = torch.tensor(list(s.counters()) + [s.energy()], dtype=torch.float64, device="cuda")
-            dist.all_reduce(acc)
+            mine_counts = list(s.counters())
+            acc = torch.tensor(mine_counts + [s.energy()], dtype=torch.float64, device="cuda")
+            per_rank = [torch.zeros_like(acc) for _ in range(world)]
+            dist.all_gather(per_rank, acc)
+            acc = torch.stack(per_rank).sum(0)
+            torch.cuda.synchronize()  # torch's collectives are done before the library's own (another communicator) start
             clus = s.cluster_stats()  # collective: clusters merged across the slab boundaries
             if rank == 0 and fail is None:
                 got = torch.cat(parts).cpu().numpy()
@@ -80,7 +84,7 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
                 if not np.array_equal(got, one.download()):
                     fail = "spins differ from the 1-GPU run"
                 elif [int(acc[0]), int(acc[1])] != [a, b]:
-                    fail = "counters differ"
+                    fail = "counters differ: per rank %s, 1 GPU %s" % ([tuple(int(v) for v in t[:2].tolist()) for t in per_rank], (a, b))
                 elif float(acc[2]) != one.energy():
                     fail = "energy differs"
                 else:
