@@ -31,3 +31,33 @@ def test_reference_arm_other_ranks_do_no_work():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_gpu_arm_fails_loudly_without_a_device():
+    """No CPU fallback: on a box without CUDA the product arm of bench.py refuses to run."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--no-cpu", "--no-extra",
+                          "--no-plugin"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0 and "needs a CUDA device" in (out.stderr + out.stdout)
+
+
+def test_workload_tables_are_consistent():
+    """every bench workload has a traffic figure from a committed ncu capture and a CPU sample size;
+    the multi-GPU check's cases split into even slabs at 2, 4 and 8 ranks."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from spparks_b200.selfcheck import cases
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert bench.DEFAULT_WORKLOAD == "potts_neighonly_sc26n_1024"
+    for name, w in bench.WORKLOADS.items():
+        assert traffic.get(name, 0) > 0, name
+        assert bench.nsites(w["lattice"], w["cpu_n"]) * 148 < 4e9  # the reference needs ~148 B/site on the host
+        cfg = bench.make_config(name, w, 1)
+        assert cfg["B_alg_bytes_per_site_update"] == 4 * (bench.NCOLORS[w["lattice"]] + 1)
+    for world in (2, 4, 8):
+        for model, lat, n, q, T in cases(world):
+            d = n[2] if lat.startswith("sc") else n[1]
+            assert d % world == 0 and (d // world) % 2 == 0 and d // world >= (2 if lat.startswith("sc") else 4)
