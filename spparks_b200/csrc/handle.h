@@ -68,6 +68,7 @@ struct spk_cuda_handle {
   // values per site that the kernels report (kstat), read back without blocking after every sweep.
   int neigh_mode = 2;            // 0 chain, 1 adaptive, 2 auto
   bool neigh_adaptive = false;   // current choice
+  double neigh_switch = 2.9;     // mean distinct neighbour values at which the variants break even (SPK_CUDA_NEIGH_SWITCH)
   unsigned long long *kstat = nullptr;       // device: sum of nevent
   unsigned long long *kstat_host = nullptr;  // pinned: [0] copy of *kstat, [1] attempts it covers
   cudaEvent_t ev_kstat = nullptr;

@@ -224,11 +224,6 @@ int build_tensor_map(spk_cuda_handle *h) {
   return 0;
 }
 
-// Candidate-list apps on sc/26n: choose between the all-pairs chain (cost independent of the
-// lattice) and candidate elimination (cost proportional to the distinct neighbour values) from
-// the mean nevent the kernels accumulate in h->kstat.  Called at the first colour of a sweep;
-// never blocks: the statistic is copied to pinned memory behind the launches already queued and
-// picked up one or two sweeps later.  Both variants give identical spins, only the speed differs.
 // ---- the two copies of an eligible lattice (int32 canonical, 16-bit shadow): exactly one may be
 // stale; conversions cover the ghost planes too, so `ghosts_valid` speaks for both
 int ensure_canon(spk_cuda_handle *h) {
@@ -282,6 +277,11 @@ void neigh_mode_reset(spk_cuda_handle *h) {
   h->kstat_attempt0 = h->nattempt_base + h->nattempt;
 }
 
+// Candidate-list apps on sc/26n: choose between the all-pairs chain (cost independent of the
+// lattice) and candidate elimination (cost proportional to the distinct neighbour values) from
+// the mean nevent the kernels accumulate in h->kstat.  Called at the first colour of a sweep;
+// never blocks: the statistic is copied to pinned memory behind the launches already queued and
+// picked up one or two sweeps later.  Both variants give identical spins, only the speed differs.
 int neigh_mode_update(spk_cuda_handle *h) {
   if (!h->kstat || h->neigh_mode != 2) return 0;
   if (h->kstat_pending && cudaEventQuery(h->ev_kstat) == cudaSuccess) {
@@ -290,9 +290,8 @@ int neigh_mode_update(spk_cuda_handle *h) {
     else if (h->kstat_host[1] > 0) {
       h->kstat_mean = (double)h->kstat_host[0] / (double)h->kstat_host[1];
       // hysteresis around the measured break-even (SPK_CUDA_NEIGH_SWITCH, distinct values per site)
-      static const double sw = [] { const char *e = getenv("SPK_CUDA_NEIGH_SWITCH"); const double v = e ? atof(e) : 0.0; return v > 0.0 ? v : 2.9; }();
-      if (h->kstat_mean < sw - 0.25) h->neigh_adaptive = true;
-      else if (h->kstat_mean > sw + 0.25) h->neigh_adaptive = false;
+      if (h->kstat_mean < h->neigh_switch - 0.25) h->neigh_adaptive = true;
+      else if (h->kstat_mean > h->neigh_switch + 0.25) h->neigh_adaptive = false;
     }
   }
   cudaGetLastError();  // cudaErrorNotReady of the query is not an error
@@ -538,6 +537,10 @@ int spk_cuda_create(const spk_cuda_desc *desc, spk_cuda_handle **out) {
     const char *nm = getenv("SPK_CUDA_NEIGH_MODE");
     h->neigh_mode = !nm ? 2 : !strcmp(nm, "chain") ? 0 : !strcmp(nm, "adaptive") ? 1 : 2;
     h->neigh_adaptive = h->neigh_mode == 1;
+    if (const char *e = getenv("SPK_CUDA_NEIGH_SWITCH")) {
+      const double v = atof(e);
+      if (v > 0.0) h->neigh_switch = v;
+    }
     if (cudaMalloc(&h->kstat, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(h->kstat, 0, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost(&h->kstat_host, 2 * sizeof(unsigned long long)) != cudaSuccess ||
