@@ -50,6 +50,8 @@ struct spk_cuda_handle {
   bool smem_attr_set[17] = {};  // dynamic shared memory opt-in done: [0] tile2d, [1..8] stream variants
   uint32_t *cl_label = nullptr, *cl_size = nullptr;  // diag_style cluster: union-find parents, volumes / ids per root
   uint32_t *cl_blocksum = nullptr;
+  long long *cl_dvol = nullptr;   // ordered cluster volumes (spk_cuda_cluster_ids), capacity cl_dvol_cap
+  size_t cl_dvol_cap = 0;
   unsigned long long *cl_count = nullptr;             // [0] ncluster, [1] (as double) sum of radii
   // clusters across slabs: 64-bit global labels / merged volumes per local root, boundary-layer
   // label buffers (out_lo, out_hi, ghost_lo, ghost_hi), foreign-root pairs, flags

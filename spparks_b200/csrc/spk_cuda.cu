@@ -590,6 +590,7 @@ int spk_cuda_destroy(spk_cuda_handle *h) {
   if (h->kstat_host) cudaFreeHost(h->kstat_host);
   if (h->ev_kstat) cudaEventDestroy(h->ev_kstat);
   cudaFree(h->cl_label); cudaFree(h->cl_size); cudaFree(h->cl_blocksum); cudaFree(h->cl_count);
+  cudaFree(h->cl_dvol);
   cudaFree(h->cl_glabel); cudaFree(h->cl_gsize); cudaFree(h->cl_layer); cudaFree(h->cl_pairs); cudaFree(h->cl_flags);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->mask_base);
@@ -1501,8 +1502,16 @@ int spk_cuda_cluster_ids(spk_cuda_handle *h, int32_t *ids, int64_t *volumes, int
   if (volumes && nvolumes < (int64_t)nc) return fail("volumes has room for %lld clusters, %llu found", (long long)nvolumes, nc);
   const long long n = h->nlocal;
   const int nb = (int)((n + CL_TILE - 1) / CL_TILE);
-  long long *dvol = nullptr;
-  CU(cudaMalloc(&dvol, (size_t)nc * sizeof(long long)));
+  // ordered volume list: a buffer kept with the handle and grown when more clusters turn up
+  if ((size_t)nc > h->cl_dvol_cap) {
+    cudaFree(h->cl_dvol);
+    h->cl_dvol = nullptr;
+    h->cl_dvol_cap = 0;
+    const size_t cap = (size_t)nc + (size_t)nc / 4 + 1024;
+    CU(cudaMalloc(&h->cl_dvol, cap * sizeof(long long)));
+    h->cl_dvol_cap = cap;
+  }
+  long long *dvol = h->cl_dvol;
   cluster_scan_blocksums<<<nb, 256, 0, h->stream>>>(h->cl_label, n, h->cl_blocksum);
   cluster_scan_offsets<<<1, 1024, 0, h->stream>>>(h->cl_blocksum, nb);
   cluster_scan_apply<<<nb, 256, 0, h->stream>>>(h->cl_label, h->cl_size, n, h->cl_blocksum, dvol);
@@ -1519,7 +1528,6 @@ int spk_cuda_cluster_ids(spk_cuda_handle *h, int32_t *ids, int64_t *volumes, int
       e = cudaMemcpyAsync(ids, h->cl_label, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(dvol);
   if (e != cudaSuccess) return fail("cluster ids: %s", cudaGetErrorString(e));
   return 0;
 }
