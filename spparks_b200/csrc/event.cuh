@@ -113,6 +113,11 @@ template <int NN> __device__ __forceinline__ int unlike(const int (&v)[NN], int 
   // two accumulator chains (the sites of a strip interleave, so four chains are in flight); the
   // first compare of each chain writes its result directly instead of adding to a zeroed register
   int e[2];
+#ifdef SPK_HOST_SHIM  // host build of tests/host_shim: the same count without PTX
+  e[0] = e[1] = 0;
+  for (int n = 0; n < NN; n++) e[n & 1] += (v[n] != value) ? one : 0;
+  return NN > 1 ? e[0] + e[1] : e[0];
+#else
 #pragma unroll
   for (int n = 0; n < NN; n++) {
     if (n < 2)
@@ -123,6 +128,7 @@ template <int NN> __device__ __forceinline__ int unlike(const int (&v)[NN], int 
           : "+r"(e[n & 1]) : "r"(v[n]), "r"(value), "r"(one));
   }
   return NN > 1 ? e[0] + e[1] : e[0];
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
