@@ -53,6 +53,12 @@ def load():
         raise SpkCudaError("libspparks_cuda.so not built (%s); run `make -C spparks_b200/csrc` or "
                            "__graft_entry__.build()" % LIB_PATH)
     L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    # tests/host_shim builds the library's sources for the host against a CUDA emulator (test
+    # infrastructure: it lets the CPU test tier run the kernels).  It is not a way to run the product:
+    # only a test that says so may load it.
+    if hasattr(L, "spk_cuda_emulated") and os.environ.get("SPK_CUDA_ALLOW_EMULATOR") != "1":
+        raise SpkCudaError("%s is the emulated test build of the library; the product needs the CUDA build "
+                           "(spparks_b200/lib/libspparks_cuda.so) and a GPU" % LIB_PATH)
     vp, i32p, i64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)
     dp = C.POINTER(C.c_double)
     L.spk_cuda_last_error.restype = C.c_char_p

@@ -33,8 +33,13 @@ struct Bits2dArgs {
 // acc <- 2*acc + (w2 > thr): the carry of w2 + ~thr (= w2 - thr - 1 + 2^32) shifted in, two
 // instructions per compare (an add.cc / addc pair: plain extended-precision addition)
 __device__ __forceinline__ void shift_in_reject(uint32_t &acc, uint32_t not_thr, uint32_t w2) {
+#ifdef SPK_HOST_SHIM  // host build of tests/host_shim: the same carry without PTX
+  const uint32_t sum = w2 + not_thr;
+  acc = acc + acc + (sum < w2 ? 1u : 0u);
+#else
   uint32_t tmp;
   asm("{\n\tadd.cc.u32 %1, %2, %3;\n\taddc.u32 %0, %0, %0;\n\t}" : "+r"(acc), "=r"(tmp) : "r"(w2), "r"(not_thr));
+#endif
 }
 
 template <int MODEL>

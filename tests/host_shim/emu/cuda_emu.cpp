@@ -1,0 +1,595 @@
+// TEST INFRASTRUCTURE.  Host implementation of cuda_emu.h / cuda_runtime.h / cuda.h (see cuda_emu.h).
+#include <cxxabi.h>
+#include <dlfcn.h>
+#include <pthread.h>
+#include <sys/mman.h>
+#include <time.h>
+#include <ucontext.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "cuda.h"
+#include "cuda_runtime.h"
+
+namespace emu {
+
+thread_local Tls *tlsp = nullptr;
+dim3 bdim, gdim;
+
+namespace {
+constexpr size_t SMEM_MAX = 232448;     // 227 KB: the opt-in maximum of dynamic shared memory per CTA on sm_100
+constexpr size_t FIBER_STACK = 256 << 10;
+constexpr long STALL_LIMIT = 4000000;   // yields of waiting fibers without any progress in the CTA: a deadlock
+
+size_t smem_limit = 48 * 1024;  // raised by cudaFuncSetAttribute(MaxDynamicSharedMemorySize)
+cudaError_t last_error = cudaSuccess;
+
+struct Fiber {
+  ucontext_t ctx;
+  Tls tls;
+  bool done = false;
+  void *stack = nullptr;
+};
+struct WarpState {
+  int lanes = 32, alive = 32, count = 0;
+  unsigned gen = 0;
+  uint64_t slot[32];
+};
+// one worker = one OS thread = one CTA at a time
+struct Worker {
+  ucontext_t main_ctx;
+  std::vector<Fiber> fibers;
+  int n = 0, alive = 0, cur = 0;
+  int bar_count = 0;
+  unsigned bar_gen = 0;
+  WarpState warps[32];
+  long stalled = 0;
+  unsigned char *smem = nullptr;
+  const std::function<void()> *body = nullptr;
+};
+thread_local Worker *W = nullptr;
+
+void deadlock(const char *what) {
+  fprintf(stderr, "cuda_emu: CTA (%u,%u,%u): no thread can make progress (%s): divergent barrier or a wait that is never satisfied\n",
+          tlsp->bid.x, tlsp->bid.y, tlsp->bid.z, what);
+  abort();
+}
+void progress() { W->stalled = 0; }
+
+// switch to the next fiber of the CTA that has not finished (round robin)
+void yield_fiber(const char *what) {
+  Worker *w = W;
+  if (++w->stalled > STALL_LIMIT) deadlock(what);
+  const int from = w->cur;
+  int to = from;
+  do { to = to + 1 == w->n ? 0 : to + 1; } while (w->fibers[to].done && to != from);
+  if (to == from) return;
+  w->cur = to;
+  tlsp = &w->fibers[to].tls;
+  swapcontext(&w->fibers[from].ctx, &w->fibers[to].ctx);
+}
+
+void barrier_release_if_complete(Worker *w) {
+  if (w->alive > 0 && w->bar_count == w->alive) {  // threads that have exited count as arrived
+    w->bar_count = 0;
+    w->bar_gen++;
+    progress();
+  }
+}
+void warp_release_if_complete(WarpState &ws) {
+  if (ws.alive > 0 && ws.count == ws.alive) {
+    ws.count = 0;
+    ws.gen++;
+    progress();
+  }
+}
+
+void fiber_main() {
+  Worker *w = W;
+  (*w->body)();
+  // the thread has exited: it no longer takes part in barriers
+  w = W;
+  Fiber &f = w->fibers[w->cur];
+  f.done = true;
+  w->alive--;
+  progress();
+  WarpState &ws = w->warps[f.tls.warp];
+  ws.alive--;
+  barrier_release_if_complete(w);
+  warp_release_if_complete(ws);
+  if (w->alive == 0) {
+    setcontext(&w->main_ctx);
+  } else {
+    int to = w->cur;
+    do { to = to + 1 == w->n ? 0 : to + 1; } while (w->fibers[to].done);
+    w->cur = to;
+    tlsp = &w->fibers[to].tls;
+    setcontext(&w->fibers[to].ctx);
+  }
+}
+
+void run_cta(Worker *w, dim3 block, dim3 bid, const std::function<void()> *body) {
+  const int n = (int)(block.x * block.y * block.z);
+  if ((int)w->fibers.size() < n) {
+    const size_t old = w->fibers.size();
+    w->fibers.resize((size_t)n);
+    for (size_t i = old; i < (size_t)n; i++) {
+      void *st = mmap(nullptr, FIBER_STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
+      if (st == MAP_FAILED) { fprintf(stderr, "cuda_emu: cannot allocate a fiber stack\n"); abort(); }
+      w->fibers[i].stack = st;
+    }
+  }
+  w->n = w->alive = n;
+  w->cur = 0;
+  w->bar_count = 0;
+  w->stalled = 0;
+  w->body = body;
+  const int nwarps = (n + 31) / 32;
+  for (int q = 0; q < nwarps; q++) {
+    WarpState &ws = w->warps[q];
+    ws.lanes = ws.alive = std::min(32, n - 32 * q);
+    ws.count = 0;
+  }
+  for (int i = 0; i < n; i++) {
+    Fiber &f = w->fibers[(size_t)i];
+    f.done = false;
+    f.tls.lin = i;
+    f.tls.lane = i & 31;
+    f.tls.warp = i >> 5;
+    f.tls.tid = dim3(i % block.x, (i / block.x) % block.y, i / (block.x * block.y));
+    f.tls.bid = bid;
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = FIBER_STACK;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, fiber_main, 0);
+  }
+  tlsp = &w->fibers[0].tls;
+  swapcontext(&w->main_ctx, &w->fibers[0].ctx);  // returns when the last thread of the CTA has exited
+  tlsp = nullptr;
+}
+
+// ---- worker pool -----------------------------------------------------------------------------------
+struct Pool {
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  std::vector<std::thread> threads;
+  unsigned long job = 0;  // generation of the current launch
+  int running = 0;
+  dim3 grid, block;
+  const std::function<void()> *body = nullptr;
+  std::atomic<long long> next{0};
+  long long total = 0;
+  bool stop = false;
+};
+Pool &pool = *new Pool;  // never destroyed: the workers are detached and live until the process ends
+
+void worker_loop() {
+  Worker me;
+  if (posix_memalign((void **)&me.smem, 1024, SMEM_MAX) != 0) abort();
+  W = &me;
+  unsigned long seen = 0;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(pool.mu);
+      pool.cv_job.wait(lk, [&] { return pool.stop || pool.job != seen; });
+      if (pool.stop) return;
+      seen = pool.job;
+    }
+    memset(me.smem, 0xCB, SMEM_MAX);  // shared memory is not initialised
+    for (;;) {
+      const long long c = pool.next.fetch_add(1);
+      if (c >= pool.total) break;
+      const dim3 bid((unsigned)(c % pool.grid.x), (unsigned)((c / pool.grid.x) % pool.grid.y),
+                     (unsigned)(c / ((long long)pool.grid.x * pool.grid.y)));
+      run_cta(&me, pool.block, bid, pool.body);
+    }
+    {
+      std::lock_guard<std::mutex> lk(pool.mu);
+      if (--pool.running == 0) pool.cv_done.notify_all();
+    }
+  }
+}
+
+std::map<std::string, long> launch_log;  // kernel (as written at the launch site) -> launches, under pool.mu
+const bool trace = getenv("SPK_EMU_TRACE") != nullptr;
+
+// the instantiation behind a launch: the demangled symbol of the kernel function (template arguments as
+// values), or the text of the launch site if the symbol cannot be resolved
+std::string kernel_name(const char *label, const void *fn) {
+  Dl_info info;
+  if (fn && dladdr(fn, &info) && info.dli_sname && info.dli_saddr == fn) {
+    int status = 0;
+    char *d = abi::__cxa_demangle(info.dli_sname, nullptr, nullptr, &status);
+    if (status == 0 && d) {
+      std::string s(d);
+      free(d);
+      const size_t paren = s.find('(');  // drop the parameter list and the return type
+      if (paren != std::string::npos) s.resize(paren);
+      if (s.rfind("void ", 0) == 0) s.erase(0, 5);
+      return s;
+    }
+  }
+  return label;
+}
+
+int pool_size() {
+  static const int n = [] {
+    const char *e = getenv("SPK_EMU_WORKERS");
+    int v = e ? atoi(e) : 0;
+    if (v <= 0) v = (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(v, 64));
+  }();
+  return n;
+}
+}  // namespace
+
+void syncthreads() {
+  Worker *w = W;
+  const unsigned gen = w->bar_gen;
+  w->bar_count++;
+  barrier_release_if_complete(w);
+  while (W->bar_gen == gen) yield_fiber("__syncthreads");
+}
+
+void warp_gather(uint64_t mine, uint64_t (&all)[32]) {
+  WarpState &ws = W->warps[tlsp->warp];
+  const int lane = tlsp->lane;
+  // phase 1: everybody deposits; phase 2: everybody has read (nobody deposits the next value earlier)
+  ws.slot[lane] = mine;
+  unsigned gen = ws.gen;
+  ws.count++;
+  warp_release_if_complete(ws);
+  while (ws.gen == gen) yield_fiber("warp collective");
+  for (int l = 0; l < 32; l++) all[l] = l < ws.lanes ? ws.slot[l] : 0;
+  gen = ws.gen;
+  ws.count++;
+  warp_release_if_complete(ws);
+  while (ws.gen == gen) yield_fiber("warp collective");
+}
+uint64_t warp_exchange(uint64_t mine, int src_lane) {
+  uint64_t all[32];
+  warp_gather(mine, all);
+  return all[src_lane];
+}
+
+unsigned char *dynamic_smem() { return W->smem; }
+
+void launch(const char *label, const void *fn, dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body) {
+  const long long n = (long long)block.x * block.y * block.z;
+  if (n <= 0 || n > 1024 || block.z > 64 || grid.x == 0 || grid.y == 0 || grid.z == 0 || grid.y > 65535 || grid.z > 65535 ||
+      smem_bytes > smem_limit) {
+    fprintf(stderr, "cuda_emu: %s: invalid launch configuration grid (%u,%u,%u) block (%u,%u,%u) smem %zu (limit %zu)\n", label,
+            grid.x, grid.y, grid.z, block.x, block.y, block.z, smem_bytes, smem_limit);
+    last_error = cudaErrorInvalidValue;
+    return;
+  }
+  const std::string kernel = kernel_name(label, fn);
+  std::unique_lock<std::mutex> lk(pool.mu);
+  launch_log[kernel]++;
+  if (trace) fprintf(stderr, "cuda_emu: %s grid (%u,%u,%u) block (%u,%u,%u) smem %zu\n", kernel.c_str(), grid.x, grid.y, grid.z, block.x,
+                     block.y, block.z, smem_bytes);
+  if (pool.threads.empty())
+    for (int i = 0; i < pool_size(); i++) {
+      pool.threads.emplace_back(worker_loop);
+      pool.threads.back().detach();
+    }
+  bdim = block;
+  gdim = grid;
+  pool.grid = grid;
+  pool.block = block;
+  pool.body = &body;
+  pool.total = (long long)grid.x * grid.y * grid.z;
+  pool.next = 0;
+  pool.running = (int)pool.threads.size();
+  pool.job++;
+  pool.cv_job.notify_all();
+  pool.cv_done.wait(lk, [&] { return pool.running == 0; });
+}
+
+uint64_t globaltimer() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+
+// ---- mbarrier (arrival count 1) -------------------------------------------------------------------
+// word: bits 0..30 number of completed phases, bit 31 "the pending arrival of this phase has
+// happened" (mbarrier.arrive.expect_tx), bits 32..63 outstanding transaction bytes (signed).
+// The phase completes when the arrival has happened and the transaction count is back to zero.
+// The word lives in the CTA's shared memory and only that CTA's fibers (one OS thread) touch it.
+namespace {
+void mb_update(uint64_t *bar, int64_t tx_delta, bool arrive) {
+  uint32_t lo = (uint32_t)*bar;
+  int32_t tx = (int32_t)(*bar >> 32);
+  tx += (int32_t)tx_delta;
+  if (arrive) {
+    if (lo & 0x80000000u) {
+      fprintf(stderr, "cuda_emu: second arrival on an mbarrier of count 1 within one phase\n");
+      abort();
+    }
+    lo |= 0x80000000u;
+  }
+  if ((lo & 0x80000000u) && tx == 0) {
+    lo = ((lo & 0x7FFFFFFFu) + 1u) & 0x7FFFFFFFu;
+    progress();
+  }
+  *bar = ((uint64_t)(uint32_t)tx << 32) | lo;
+}
+}  // namespace
+void mbar_init(uint64_t *bar, int count) {
+  if (count != 1) {
+    fprintf(stderr, "cuda_emu: mbarrier arrival count %d not supported\n", count);
+    abort();
+  }
+  *bar = 0;
+}
+void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { mb_update(bar, (int64_t)bytes, true); }
+void mbar_wait(uint64_t *bar, uint32_t parity) {
+  // try_wait.parity(p) succeeds once the phase of parity p has completed: the current phase has the other parity
+  while ((((uint32_t)*(volatile uint64_t *)bar) & 1u) == (parity & 1u)) yield_fiber("mbarrier wait");
+}
+
+// ---- tensor maps and the bulk tensor copy ---------------------------------------------------------
+namespace {
+struct TmapDesc {
+  uint64_t magic;
+  unsigned char *base;
+  uint32_t rank, elem;
+  uint64_t dims[5];
+  uint64_t strides[5];  // bytes; strides[0] = elem
+  uint32_t box[5];
+};
+static_assert(sizeof(TmapDesc) <= sizeof(CUtensorMap), "descriptor must fit the opaque tensor map");
+constexpr uint64_t TMAP_MAGIC = 0x544D41505F454D55ull;
+
+// cuTensorMapEncodeTiled with the argument checks of the driver API reference
+CUresult encode_tiled(CUtensorMap *map, CUtensorMapDataType dtype, cuuint32_t rank, void *base, const cuuint64_t *dims,
+                      const cuuint64_t *strides, const cuuint32_t *box, const cuuint32_t *estr, CUtensorMapInterleave il,
+                      CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  static const uint32_t esize[] = {1, 2, 4, 4, 8, 8};
+  if (!map || rank < 1 || rank > 5 || (int)dtype < 0 || (int)dtype > 5 || il != CU_TENSOR_MAP_INTERLEAVE_NONE ||
+      sw != CU_TENSOR_MAP_SWIZZLE_NONE)
+    return CUDA_ERROR_INVALID_VALUE;
+  const uint32_t elem = esize[(int)dtype];
+  if (!base || ((uintptr_t)base & 15u)) return CUDA_ERROR_INVALID_VALUE;  // globalAddress: 16-byte aligned
+  TmapDesc d;
+  memset(&d, 0, sizeof d);
+  d.magic = TMAP_MAGIC;
+  d.base = (unsigned char *)base;
+  d.rank = rank;
+  d.elem = elem;
+  for (uint32_t i = 0; i < rank; i++) {
+    if (dims[i] == 0 || dims[i] > (1ull << 32)) return CUDA_ERROR_INVALID_VALUE;  // globalDim: non-zero, <= 2^32
+    if (box[i] == 0 || box[i] > 256) return CUDA_ERROR_INVALID_VALUE;              // boxDim: non-zero, <= 256
+    if (estr[i] == 0 || estr[i] > 8) return CUDA_ERROR_INVALID_VALUE;
+    if (estr[i] != 1) return CUDA_ERROR_INVALID_VALUE;  // not emulated
+    d.dims[i] = dims[i];
+    d.box[i] = box[i];
+    if (i == 0) d.strides[0] = elem;
+    else {
+      const uint64_t s = strides[i - 1];
+      if (s == 0 || (s & 15u) || s >= (1ull << 40)) return CUDA_ERROR_INVALID_VALUE;  // globalStrides: multiple of 16, < 2^40
+      d.strides[i] = s;
+    }
+  }
+  if (((uint64_t)box[0] * elem) & 15u) return CUDA_ERROR_INVALID_VALUE;  // inner box extent: multiple of 16 bytes
+  memset(map, 0, sizeof *map);
+  memcpy(map, &d, sizeof d);
+  return CUDA_SUCCESS;
+}
+}  // namespace
+
+void tma_load(void *dst, const void *tensor_map, uint64_t *bar, const int *coord, int rank) {
+  TmapDesc d;
+  memcpy(&d, tensor_map, sizeof d);
+  if (d.magic != TMAP_MAGIC || (int)d.rank != rank) {
+    fprintf(stderr, "cuda_emu: bulk tensor copy with an invalid tensor map\n");
+    abort();
+  }
+  unsigned char *out = (unsigned char *)dst;
+  uint64_t total = d.elem;
+  for (int i = 0; i < rank; i++) total *= d.box[i];
+  if (((uintptr_t)out & 127u) || out < W->smem || out + total > W->smem + SMEM_MAX) {  // shared-memory destination: 128-byte aligned
+    fprintf(stderr, "cuda_emu: bulk tensor copy destination misaligned or outside shared memory\n");
+    abort();
+  }
+  uint32_t idx[5] = {0, 0, 0, 0, 0};
+  for (uint64_t e = 0; e < total / d.elem; e++) {
+    bool inside = true;
+    uint64_t off = 0;
+    for (int i = 0; i < rank; i++) {
+      const long long c = (long long)coord[i] + idx[i];
+      if (c < 0 || c >= (long long)d.dims[i]) inside = false;
+      else off += (uint64_t)c * d.strides[i];
+    }
+    if (inside) memcpy(out + e * d.elem, d.base + off, d.elem);
+    else memset(out + e * d.elem, 0, d.elem);  // out-of-bound elements are filled with zeros
+    for (int i = 0; i < rank; i++) {
+      if (++idx[i] < d.box[i]) break;
+      idx[i] = 0;
+    }
+  }
+  mb_update(bar, -(int64_t)total, false);  // complete_tx
+}
+
+}  // namespace emu
+
+void __nanosleep(unsigned) { std::this_thread::yield(); }
+
+// ---- runtime API ------------------------------------------------------------------------------------
+struct emuStream_st { int dummy; };
+struct emuEvent_st { std::chrono::steady_clock::time_point t; bool recorded = false; };
+
+const char *cudaGetErrorString(cudaError_t e) {
+  switch (e) {
+    case cudaSuccess: return "no error";
+    case cudaErrorInvalidValue: return "invalid argument";
+    case cudaErrorMemoryAllocation: return "out of memory";
+    case cudaErrorNotReady: return "not ready";
+    case cudaErrorNotSupported: return "operation not supported (cuda_emu)";
+    default: return "unknown error";
+  }
+}
+cudaError_t cudaGetLastError() {
+  const cudaError_t e = emu::last_error;
+  emu::last_error = cudaSuccess;
+  return e;
+}
+cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int dev) { return dev == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t emuMalloc(void **p, size_t bytes) {
+  void *q = nullptr;
+  if (posix_memalign(&q, 256, bytes ? bytes : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  memset(q, 0xCD, bytes);  // device memory is not initialised
+  *p = q;
+  return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t emuMallocHost(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) {
+  memmove(dst, src, bytes);
+  return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *p, int value, size_t bytes, cudaStream_t) { memset(p, value, bytes); return cudaSuccess; }
+cudaError_t cudaMemset(void *p, int value, size_t bytes) { memset(p, value, bytes); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new emuStream_st; return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emuEvent_st; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new emuEvent_st; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+  e->t = std::chrono::steady_clock::now();
+  e->recorded = true;
+  return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+  if (!a->recorded || !b->recorded) return cudaErrorInvalidValue;
+  *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+  return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+cudaError_t cudaGetDriverEntryPoint(const char *symbol, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *status) {
+  if (!strcmp(symbol, "cuTensorMapEncodeTiled")) {
+    *fn = (void *)&emu::encode_tiled;
+    if (status) *status = cudaDriverEntryPointSuccess;
+    return cudaSuccess;
+  }
+  *fn = nullptr;
+  if (status) *status = cudaDriverEntryPointSymbolNotFound;
+  return cudaErrorInvalidValue;
+}
+cudaError_t emuFuncSetAttribute(int attr, int value) {
+  if (attr != (int)cudaFuncAttributeMaxDynamicSharedMemorySize || value < 0 || (size_t)value > emu::SMEM_MAX)
+    return cudaErrorInvalidValue;
+  // the limit is per kernel on the GPU; the emulator keeps the largest request (every launch passes its own size)
+  emu::smem_limit = std::max(emu::smem_limit, (size_t)value);
+  return cudaSuccess;
+}
+
+// ---- what the tests ask the emulator itself -----------------------------------------------------------
+extern "C" {
+// marks the library as the emulated build (spparks_b200/_lib.py refuses it unless a test opts in)
+int spk_cuda_emulated(void) { return 1; }
+// "kernel<args> count" lines of every kernel launched since the last reset; returns the length needed
+size_t spk_emu_launch_log(char *buf, size_t cap) {
+  std::string out;
+  {
+    std::lock_guard<std::mutex> lk(emu::pool.mu);
+    for (const auto &kv : emu::launch_log) out += kv.first + "\t" + std::to_string(kv.second) + "\n";
+  }
+  if (buf && cap) {
+    const size_t n = std::min(cap - 1, out.size());
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return out.size() + 1;
+}
+// checks of the emulator itself (0 = all passed, otherwise the number of the failed check)
+int spk_emu_selftest(void) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, nullptr) != cudaSuccess) return 1;
+  encode_fn enc = (encode_fn)fn;
+  int32_t *buf = nullptr;
+  if (cudaMalloc(&buf, 64 * 32 * 4) != cudaSuccess) return 2;
+  for (int i = 0; i < 64 * 32; i++) buf[i] = i + 1;
+  CUtensorMap m;
+  cuuint64_t dims[2] = {64, 32}, strides[1] = {64 * 4};
+  cuuint32_t box[2] = {16, 4}, estr[2] = {1, 1};
+  auto encode = [&](const cuuint32_t *b, const cuuint64_t *st, void *base) {
+    return enc(&m, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, base, dims, st, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  const cuuint32_t wide[2] = {272, 4}, ragged[2] = {6, 4};
+  const cuuint64_t odd_stride[1] = {64 * 4 + 4};
+  if (encode(wide, strides, buf) == CUDA_SUCCESS) return 3;        // box extent above 256
+  if (encode(ragged, strides, buf) == CUDA_SUCCESS) return 4;      // inner box extent not a multiple of 16 bytes
+  if (encode(box, odd_stride, buf) == CUDA_SUCCESS) return 5;      // stride not a multiple of 16 bytes
+  if (encode(box, strides, buf + 1) == CUDA_SUCCESS) return 6;     // base not 16-byte aligned
+  if (encode(box, strides, buf) != CUDA_SUCCESS) return 7;
+  // a box that hangs over the low corner: zeros outside, the tensor's elements inside; one thread
+  // issues, everybody waits on the mbarrier, the barrier is reused with the other parity
+  int bad = 0;
+  emu::launch("selftest", nullptr, dim3(3), dim3(64), 16 * 4 * 4 + 64, [&]() {
+    unsigned char *smem = emu::dynamic_smem();
+    int32_t *tile = reinterpret_cast<int32_t *>(smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 16 * 4 * 4);
+    if (threadIdx.x == 0) emu::mbar_init(bar, 1);
+    __syncthreads();
+    for (int round = 0; round < 2; round++) {
+      const int cx = round ? 56 : -4, cy = round ? 30 : -1;
+      if (threadIdx.x == 0) {
+        emu::mbar_expect_tx(bar, 16 * 4 * 4);
+        const int c[2] = {cx, cy};
+        emu::tma_load(tile, &m, bar, c, 2);
+      }
+      emu::mbar_wait(bar, (uint32_t)round);
+      const int t = (int)threadIdx.x, x = cx + t % 16, y = cy + t / 16;
+      const int want = (x < 0 || x >= 64 || y < 0 || y >= 32) ? 0 : y * 64 + x + 1;
+      if (tile[t] != want) __atomic_fetch_add(&bad, 1, __ATOMIC_SEQ_CST);
+      __syncthreads();
+    }
+    // warp collectives
+    const int lane = (int)threadIdx.x & 31;
+    if (__reduce_add_sync(0xffffffffu, lane) != 496) __atomic_fetch_add(&bad, 1, __ATOMIC_SEQ_CST);
+    if (__shfl_down_sync(0xffffffffu, lane, 1) != (lane < 31 ? lane + 1 : lane)) __atomic_fetch_add(&bad, 1, __ATOMIC_SEQ_CST);
+    if (__shfl_xor_sync(0xffffffffu, lane, 5) != (lane ^ 5)) __atomic_fetch_add(&bad, 1, __ATOMIC_SEQ_CST);
+    if (__match_any_sync(0xffffffffu, lane & 3) != (0x11111111u << (lane & 3))) __atomic_fetch_add(&bad, 1, __ATOMIC_SEQ_CST);
+    if (__ballot_sync(0xffffffffu, lane & 1) != 0xAAAAAAAAu) __atomic_fetch_add(&bad, 1, __ATOMIC_SEQ_CST);
+  });
+  cudaFree(buf);
+  if (bad) return 8;
+  if (__viaddmin_u16x2(0x0005FFFFu, 0xFFFB0001u, 0x00010001u) != 0x00000000u) return 9;   // 5 + (-5) = 0, 0xFFFF + 1 = 0 (mod 2^16)
+  if (__viaddmin_u16x2(0x00070003u, 0xFFFBFFFEu, 0x00010001u) != 0x00010001u) return 10;  // 2 and 1, capped at 1
+  if (__funnelshift_l(0x80000000u, 0x00000001u, 1) != 0x00000003u || __funnelshift_r(0x00000003u, 0x00000001u, 1) != 0x80000001u)
+    return 11;
+  return 0;
+}
+void spk_emu_launch_log_reset(void) {
+  std::lock_guard<std::mutex> lk(emu::pool.mu);
+  emu::launch_log.clear();
+}
+}

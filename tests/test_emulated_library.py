@@ -1,0 +1,171 @@
+"""CPU tier: the sources of libspparks_cuda compiled for the host against a CUDA emulator.
+
+tests/host_shim/build_emu.py compiles spparks_b200/csrc — the ABI, the host logic and every kernel:
+TMA streaming kernels, 16-bit and 1-bit shadows, colour-fused 2-D kernel, colour-pair launches,
+candidate elimination, strip and generic kernels, masks, clusters — with g++ against
+tests/host_shim/emu (CTAs on worker threads, the threads of a CTA as fibers that switch at
+__syncthreads / warp collectives / mbarrier waits, bulk tensor copies with the driver's argument
+checks and zero fill).  The GPU parity tests then run against that build in this container: the same
+test functions, the same oracle and reference fixtures, through the same C ABI; the plugin tests run
+the real SPPARKS binary on its `in.*` scripts with the emulated library in place of the CUDA one.
+
+What this proves: the source of the kernels and of the host logic computes the reference's results.
+What it cannot prove: anything about the hardware (timing, races inside a CTA, asynchrony of TMA and
+of peer-memory stores, ptxas) — that stays with `-m gpu` on the B200.  The emulated build is test
+infrastructure: spparks_b200/_lib.py refuses to load it unless a test opts in.
+"""
+import ctypes as C
+import importlib.util
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SPK_CUDA = os.path.join(ROOT, "plugin", "_build", "spk_cuda")
+
+
+def _build_emu():
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "host_shim", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    mod = _build_emu()
+    lib = mod.build()
+    libdir = os.path.join(mod.BUILD, "libdir")  # the plugin binary asks the loader for "libspparks_cuda.so"
+    os.makedirs(libdir, exist_ok=True)
+    link = os.path.join(libdir, "libspparks_cuda.so")
+    if not os.path.islink(link):
+        os.symlink(os.path.join("..", os.path.basename(lib)), link)
+    return lib
+
+
+def _env(emu_lib):
+    env = dict(os.environ, SPK_CUDA_LIB=emu_lib, SPK_CUDA_ALLOW_EMULATOR="1")
+    libdir = os.path.join(os.path.dirname(emu_lib), "libdir")
+    env["LD_LIBRARY_PATH"] = libdir + (":" + env["LD_LIBRARY_PATH"] if env.get("LD_LIBRARY_PATH") else "")
+    return env
+
+
+def _run_gpu_tests(emu_lib, args):
+    """`pytest -m gpu` on the given files in a fresh interpreter that loads the emulated library"""
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + args
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib), capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and " failed" not in r.stdout and " error" not in r.stdout, r.stdout[-2000:]
+    return int(m.group(1))
+
+
+def test_emulator_selftest(emu_lib):
+    """tensor-map argument checks (box extent <= 256, 16-byte rules), zero fill outside the tensor,
+    mbarrier phases, warp collectives, the restated integer intrinsics"""
+    L = C.CDLL(emu_lib)
+    assert L.spk_emu_selftest() == 0
+
+
+def test_product_loader_refuses_the_emulated_build(emu_lib):
+    code = ("import spparks_b200._lib as l\n"
+            "try:\n    l.load()\nexcept l.SpkCudaError as e:\n    print('REFUSED', e)\nelse:\n    print('LOADED')\n")
+    env = _env(emu_lib)
+    del env["SPK_CUDA_ALLOW_EMULATOR"]
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=120)
+    assert "REFUSED" in r.stdout and "LOADED" not in r.stdout, r.stdout + r.stderr
+
+
+def test_gpu_parity_tests_pass_on_the_emulated_library(emu_lib):
+    """every test of tests/test_gpu_parity.py: reference fixtures (injected half-sweeps, sector sets,
+    masked passes, strict runs), Philox sweeps through every kernel tier, shadows interleaved with
+    int32 entry points, candidate elimination, device `set site range`, error paths"""
+    assert _run_gpu_tests(emu_lib, ["tests/test_gpu_parity.py"]) >= 380
+
+
+def test_cluster_tests_pass_on_the_emulated_library(emu_lib):
+    """union-find clustering (atomics, __match_any_sync, scans) against the reference's clusters"""
+    assert _run_gpu_tests(emu_lib, ["tests/test_cluster.py", "-k", "not large"]) >= 12
+
+
+@pytest.mark.skipif(not os.path.exists(SPK_CUDA), reason="plugin/_build/spk_cuda not built (needs the reference tree)")
+def test_plugin_scripts_pass_on_the_emulated_library(emu_lib):
+    """the SPPARKS binary with the app-style plugin runs its in.* scripts against the emulated library"""
+    r = subprocess.run(["ldd", SPK_CUDA], env=_env(emu_lib), capture_output=True, text=True)
+    assert "host_shim/_build/libdir/libspparks_cuda.so" in r.stdout, r.stdout
+    assert _run_gpu_tests(emu_lib, ["tests/test_plugin.py"]) >= 20
+
+
+TIER_SCRIPT = r"""
+import ctypes as C, json, os, sys
+import numpy as np
+from spparks_b200 import LatticeSweep
+L = C.CDLL(os.environ["SPK_CUDA_LIB"])
+L.spk_emu_launch_log.restype = C.c_size_t
+def log():
+    n = L.spk_emu_launch_log(None, 0)
+    b = C.create_string_buffer(n)
+    L.spk_emu_launch_log(b, n)
+    return dict((k, int(v)) for k, v in (line.split("\t") for line in b.value.decode().splitlines()))
+out = {}
+for key, model, lat, n, q, env in json.loads(sys.argv[1]):
+    for k in [k for k in os.environ if k.startswith("SPK_CUDA_") and k not in ("SPK_CUDA_LIB", "SPK_CUDA_ALLOW_EMULATOR")]:
+        del os.environ[k]
+    os.environ.update(env)
+    L.spk_emu_launch_log_reset()
+    s = LatticeSweep(model, lat, *n, nspins=q, temperature=0.7, seed=5)
+    nb = 2 if lat == "tri" else 1
+    s.upload(np.random.default_rng(1).integers(1, (2 if model.startswith("ising") else q) + 1, size=n[0] * n[1] * n[2] * nb, dtype=np.int32))
+    s.sweeps(0, 2)
+    s.download()
+    out[key] = log()
+print("TIERS " + json.dumps(out))
+"""
+
+
+def test_every_kernel_tier_is_the_one_that_runs(emu_lib):
+    """the instantiation each configuration launches (demangled kernel symbols recorded by the emulator):
+    a parity test that passes on a silent fallback to the generic kernel would say nothing about the tuned ones.
+    Template arguments: lattice 2 sq/4n, 3 sq/8n, 4 tri, 5 sc/6n, 6 sc/26n; model 0 ising, 1 potts, 2 potts/neighonly, 3 potts/pin."""
+    cases = [
+        ["shadow16", "potts/pin", "sc/26n", (32, 16, 12), 50, {}],
+        ["int32stream", "potts", "sc/26n", (32, 16, 12), 50, {"SPK_CUDA_NO_SHADOW16": "1"}],
+        ["stream32", "potts", "sc/26n", (32, 16, 12), 70000, {}],
+        ["pair", "potts", "sc/26n", (32, 16, 12), 50, {"SPK_CUDA_PAIR": "1", "SPK_CUDA_NO_SHADOW16": "1"}],
+        ["chain", "potts/neighonly", "sc/26n", (32, 12, 14), 100, {"SPK_CUDA_NEIGH_MODE": "chain"}],
+        ["elimination", "potts/neighonly", "sc/26n", (32, 12, 14), 100, {"SPK_CUDA_NEIGH_MODE": "adaptive"}],
+        ["sc6n", "ising", "sc/6n", (16, 12, 10), 2, {}],
+        ["bits", "ising", "sq/4n", (256, 34, 1), 2, {}],
+        ["fused2d", "potts", "tri", (252, 66, 1), 9, {}],
+        ["strip", "potts", "sq/8n", (72, 18, 1), 7, {"SPK_CUDA_NO_FUSED": "1"}],
+        ["generic", "potts", "sq/8n", (34, 22, 1), 7, {}],
+    ]
+    import json
+    r = subprocess.run([sys.executable, "-c", TIER_SCRIPT, json.dumps(cases)], cwd=ROOT, env=_env(emu_lib), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    tiers = json.loads(re.search(r"TIERS (.*)", r.stdout).group(1))
+    want = {
+        "shadow16": "spk::sweep_stream16_kernel<3>",
+        "int32stream": "spk::sweep_stream_kernel<6, 1, true, true, false, 0>",
+        "stream32": "spk::sweep_stream_kernel<6, 1, true, false, false, 0>",   # Q > 65533: 32-bit compares
+        "pair": "spk::sweep_stream_kernel<6, 1, true, true, true, 0>",
+        "chain": "spk::sweep_stream_kernel<6, 2, true, true, false, 0>",
+        "elimination": "spk::sweep_stream_kernel<6, 2, true, true, false, 1>",
+        "sc6n": "spk::sweep_stream_kernel<5, 0, true, false, false, 0>",
+        "bits": "spk::sweep_bits2d_kernel<0>",
+        "fused2d": "spk::sweep_tile2d_kernel<4, 1>",
+        "strip": "spk::sweep_strip_kernel<3, 1>",
+        "generic": "spk::sweep_generic_kernel<3, 1, 0>",
+    }
+    for key, kernel in want.items():
+        assert kernel in tiers[key], (key, tiers[key])
+        sweepers = [k for k in tiers[key] if "sweep_" in k]
+        assert sweepers == [kernel], (key, tiers[key])  # nothing else swept
+    assert "spk::edge_pair_kernel<1, true>" in tiers["pair"]
+    assert tiers["shadow16"]["shadow_pack_kernel"] == 1 and tiers["shadow16"]["shadow_unpack_kernel"] == 1
+    assert tiers["bits"]["bits2d_pack_kernel"] == 1 and tiers["bits"]["bits2d_unpack_kernel"] == 1
