@@ -34,6 +34,10 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
     """Runs every case on `world` slabs and, on rank 0, on one GPU; returns "ok" or a description
     of the first failing case (the same string on every rank).  halo: "p2p" (peer-memory stores
     where available) or "nccl" (send/recv exchange)."""
+    # the tensors of the check's own plumbing live where `dist` moves them: on the GPU for NCCL; a
+    # CPU backend (gloo) is what the emulated test build of the library is driven with (tests/host_shim)
+    on_gpu = torch.cuda.is_available() and str(dist.get_backend()) != "gloo"
+    tdev = "cuda" if on_gpu else "cpu"
     old = os.environ.get("SPK_CUDA_NO_P2P")
     if halo == "nccl":
         os.environ["SPK_CUDA_NO_P2P"] = "1"
@@ -51,9 +55,9 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
                 spins[rng.random(nsites) < 0.05] = q + 1
             s = LatticeSweep(model, lat, n[0], n[1], n[2], nspins=q, temperature=T, seed=777, device=local,
                              rank=rank, nranks=world)
-            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            idt = torch.zeros(128, dtype=torch.uint8, device=tdev)
             if rank == 0:
-                idt = torch.frombuffer(bytearray(LatticeSweep.comm_id()), dtype=torch.uint8).cuda()
+                idt = torch.frombuffer(bytearray(LatticeSweep.comm_id()), dtype=torch.uint8).to(tdev)
             dist.broadcast(idt, 0)
             s.comm_init(idt.cpu().numpy().tobytes())
             fused2d = not dim3 and (n[0] * nb) % 8 == 0  # the colour-fused 2-D kernel takes rows of 8-element multiples
@@ -65,15 +69,16 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
             s.upload(spins[lo:hi])
             s.sweeps(3, 2)
             s.sweeps(5, 2)  # second call: ghosts are still valid, no re-seeding exchange
-            mine = torch.from_numpy(s.download()).cuda()
+            mine = torch.from_numpy(s.download()).to(tdev)
             parts = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(parts, mine)
             mine_counts = list(s.counters())
-            acc = torch.tensor(mine_counts + [s.energy()], dtype=torch.float64, device="cuda")
+            acc = torch.tensor(mine_counts + [s.energy()], dtype=torch.float64, device=tdev)
             per_rank = [torch.zeros_like(acc) for _ in range(world)]
             dist.all_gather(per_rank, acc)
             acc = torch.stack(per_rank).sum(0)
-            torch.cuda.synchronize()  # torch's collectives are done before the library's own (another communicator) start
+            if on_gpu:
+                torch.cuda.synchronize()  # torch's collectives are done before the library's own (another communicator) start
             clus = s.cluster_stats()  # collective: clusters merged across the slab boundaries
             if rank == 0 and fail is None:
                 got = torch.cat(parts).cpu().numpy()
@@ -93,7 +98,7 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
                         fail = "cluster statistics %r differ from the 1-GPU run's %r" % (clus, c1)
                 one.close()
             s.close()
-            flag = torch.tensor([0 if fail is None else 1], dtype=torch.int32, device="cuda")
+            flag = torch.tensor([0 if fail is None else 1], dtype=torch.int32, device=tdev)
             dist.broadcast(flag, 0)
             if log and rank == 0:
                 log("%s %s %s %s ranks %d halo %s" % ("ok" if fail is None else "FAIL", model, lat, n, world, halo))
@@ -111,9 +116,9 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
             slab = zz if dim3 else yy
             spins = np.where((xx + 3 * slab) % 8 < 3, 2 + (xx + 3 * slab) // 8 % 3, 1).astype(np.int32).reshape(-1)
             s = LatticeSweep("potts", lat, n[0], n[1], n[2], nspins=5, temperature=0.5, seed=1, device=local, rank=rank, nranks=world)
-            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            idt = torch.zeros(128, dtype=torch.uint8, device=tdev)
             if rank == 0:
-                idt = torch.frombuffer(bytearray(LatticeSweep.comm_id()), dtype=torch.uint8).cuda()
+                idt = torch.frombuffer(bytearray(LatticeSweep.comm_id()), dtype=torch.uint8).to(tdev)
             dist.broadcast(idt, 0)
             s.comm_init(idt.cpu().numpy().tobytes())
             s.upload(spins[rank * s.nlocal:(rank + 1) * s.nlocal])
@@ -127,7 +132,7 @@ def mgpu_parity(dist, rank, world, local, halo="p2p", log=None):
                 one.close()
                 if clus[0] != c1[0] or clus[1] != c1[1] or abs(clus[2] - c1[2]) > 1e-9 * c1[2]:
                     fail = "cluster statistics %r differ from the 1-GPU run's %r" % (clus, c1)
-            flag = torch.tensor([0 if fail is None else 1], dtype=torch.int32, device="cuda")
+            flag = torch.tensor([0 if fail is None else 1], dtype=torch.int32, device=tdev)
             dist.broadcast(flag, 0)
             if log and rank == 0:
                 log("%s banded clusters %s %s ranks %d: %r" % ("ok" if fail is None else "FAIL", lat, n, world, clus))

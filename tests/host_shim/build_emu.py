@@ -30,6 +30,7 @@ CSRC = os.path.join(ROOT, "spparks_b200", "csrc")
 EMU = os.path.join(HERE, "emu")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libspparks_cuda_emu.so")
+NCCL_LIB = os.path.join(BUILD, "libnccl_emu.so")  # for SPK_CUDA_NCCL_LIB: ranks = processes of this host
 UNITS = ["spk_cuda.cu", "model_ising.cu", "model_potts.cu", "model_potts_neighonly.cu", "model_potts_pin.cu",
          "model_ising_single.cu", "model_potts_neigh.cu"]
 CXXFLAGS = ["-std=c++17", "-O1", "-fPIC", "-pthread", "-w", "-fno-strict-aliasing"]
@@ -201,7 +202,7 @@ def build(jobs=None, verbose=False):
     """build (if anything changed) and return the path of the emulated library"""
     stamp_file = os.path.join(BUILD, "stamp")
     stamp = _stamp()
-    if os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+    if os.path.exists(LIB) and os.path.exists(NCCL_LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return LIB
     src = os.path.join(BUILD, "src")
     n = rewrite_sources(src)
@@ -213,6 +214,7 @@ def build(jobs=None, verbose=False):
         list(ex.map(lambda w: _compile(*w), work))
     cmd = ["g++", "-shared", "-pthread", "-o", LIB] + [w[1] for w in work] + ["-ldl"]
     subprocess.check_call(cmd)
+    subprocess.check_call(["g++"] + CXXFLAGS + ["-shared", "-I", EMU, os.path.join(EMU, "nccl_emu.cpp"), "-o", NCCL_LIB])
     open(stamp_file, "w").write(stamp)
     return LIB
 

@@ -2,6 +2,7 @@
 #include <cxxabi.h>
 #include <dlfcn.h>
 #include <pthread.h>
+#include <fcntl.h>
 #include <sys/mman.h>
 #include <time.h>
 #include <ucontext.h>
@@ -33,8 +34,59 @@ constexpr long STALL_LIMIT = 4000000;   // yields of waiting fibers without any 
 size_t smem_limit = 48 * 1024;  // raised by cudaFuncSetAttribute(MaxDynamicSharedMemorySize)
 cudaError_t last_error = cudaSuccess;
 
+// ---- fibers: a context is the stack pointer of a suspended fiber, its callee-saved registers on its stack ----
+#if defined(__x86_64__)
+extern "C" void spk_emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.hidden spk_emu_switch
+.globl spk_emu_switch
+.type spk_emu_switch,@function
+spk_emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size spk_emu_switch,.-spk_emu_switch
+)");
+struct Context {
+  void *sp = nullptr;
+  void prepare(void *stack, size_t bytes, void (*entry)()) {
+    void **top = reinterpret_cast<void **>(((uintptr_t)stack + bytes) & ~(uintptr_t)15);
+    *--top = nullptr;                            // where `entry` would return to (it never does); rsp % 16 == 8 on entry
+    *--top = reinterpret_cast<void *>(entry);    // the `ret` of the first switch jumps here
+    for (int i = 0; i < 6; i++) *--top = nullptr;  // rbp rbx r12 r13 r14 r15
+    sp = top;
+  }
+};
+inline void switch_context(Context &from, Context &to) { spk_emu_switch(&from.sp, to.sp); }
+#else  // portable, slower (two signal-mask system calls per switch)
+struct Context {
+  ucontext_t uc;
+  void prepare(void *stack, size_t bytes, void (*entry)()) {
+    getcontext(&uc);
+    uc.uc_stack.ss_sp = stack;
+    uc.uc_stack.ss_size = bytes;
+    uc.uc_link = nullptr;
+    makecontext(&uc, entry, 0);
+  }
+};
+inline void switch_context(Context &from, Context &to) { swapcontext(&from.uc, &to.uc); }
+#endif
+
 struct Fiber {
-  ucontext_t ctx;
+  Context ctx;
   Tls tls;
   bool done = false;
   void *stack = nullptr;
@@ -46,7 +98,7 @@ struct WarpState {
 };
 // one worker = one OS thread = one CTA at a time
 struct Worker {
-  ucontext_t main_ctx;
+  Context main_ctx;
   std::vector<Fiber> fibers;
   int n = 0, alive = 0, cur = 0;
   int bar_count = 0;
@@ -75,7 +127,7 @@ void yield_fiber(const char *what) {
   if (to == from) return;
   w->cur = to;
   tlsp = &w->fibers[to].tls;
-  swapcontext(&w->fibers[from].ctx, &w->fibers[to].ctx);
+  switch_context(w->fibers[from].ctx, w->fibers[to].ctx);
 }
 
 void barrier_release_if_complete(Worker *w) {
@@ -107,14 +159,15 @@ void fiber_main() {
   barrier_release_if_complete(w);
   warp_release_if_complete(ws);
   if (w->alive == 0) {
-    setcontext(&w->main_ctx);
+    switch_context(f.ctx, w->main_ctx);
   } else {
     int to = w->cur;
     do { to = to + 1 == w->n ? 0 : to + 1; } while (w->fibers[to].done);
     w->cur = to;
     tlsp = &w->fibers[to].tls;
-    setcontext(&w->fibers[to].ctx);
+    switch_context(f.ctx, w->fibers[to].ctx);
   }
+  abort();  // a finished fiber is never resumed
 }
 
 void run_cta(Worker *w, dim3 block, dim3 bid, const std::function<void()> *body) {
@@ -147,14 +200,10 @@ void run_cta(Worker *w, dim3 block, dim3 bid, const std::function<void()> *body)
     f.tls.warp = i >> 5;
     f.tls.tid = dim3(i % block.x, (i / block.x) % block.y, i / (block.x * block.y));
     f.tls.bid = bid;
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = f.stack;
-    f.ctx.uc_stack.ss_size = FIBER_STACK;
-    f.ctx.uc_link = nullptr;
-    makecontext(&f.ctx, fiber_main, 0);
+    f.ctx.prepare(f.stack, FIBER_STACK, fiber_main);
   }
   tlsp = &w->fibers[0].tls;
-  swapcontext(&w->main_ctx, &w->fibers[0].ctx);  // returns when the last thread of the CTA has exited
+  switch_context(w->main_ctx, w->fibers[0].ctx);  // returns when the last thread of the CTA has exited
   tlsp = nullptr;
 }
 
@@ -424,7 +473,10 @@ void tma_load(void *dst, const void *tensor_map, uint64_t *bar, const int *coord
 
 }  // namespace emu
 
-void __nanosleep(unsigned) { std::this_thread::yield(); }
+void __nanosleep(unsigned) {  // inside a spin on memory another process writes: not a stall of this CTA
+  if (emu::W) emu::W->stalled = 0;
+  std::this_thread::yield();
+}
 
 // ---- runtime API ------------------------------------------------------------------------------------
 struct emuStream_st { int dummy; };
@@ -445,16 +497,102 @@ cudaError_t cudaGetLastError() {
   emu::last_error = cudaSuccess;
   return e;
 }
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
-cudaError_t cudaSetDevice(int dev) { return dev == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+// ---- "device" memory --------------------------------------------------------------------------------
+// Default: the heap.  With SPK_EMU_ARENA_DIR set (multi-rank tests: one process per rank) every
+// allocation comes out of one file-backed shared mapping per process, so that cudaIpcGetMemHandle /
+// cudaIpcOpenMemHandle can hand an allocation to another process the way CUDA IPC does: the peer
+// maps the same pages, stores through the mapping are visible to the owner.
+namespace {
+constexpr size_t ARENA_BYTES = 8ull << 30;  // sparse: only touched pages exist
+struct Arena {
+  std::mutex mu;
+  unsigned char *base = nullptr;
+  std::string path;
+  std::map<size_t, size_t> used, free_;  // offset -> bytes
+  std::map<int, unsigned char *> peers;  // pid -> mapping of that process's arena
+  std::string dir;
+};
+Arena &arena = *new Arena;
+struct IpcPayload { uint64_t magic; int32_t pid; uint32_t pad; uint64_t offset, bytes; };
+static_assert(sizeof(IpcPayload) <= sizeof(cudaIpcMemHandle_t), "");
+constexpr uint64_t IPC_MAGIC = 0x4950435F454D5531ull;
+
+std::string arena_path(const std::string &dir, int pid) { return dir + "/spk_emu_arena_" + std::to_string(pid); }
+void arena_unlink() {
+  if (!arena.path.empty()) unlink(arena.path.c_str());
+}
+bool arena_enabled() {
+  static const bool on = [] {
+    const char *d = getenv("SPK_EMU_ARENA_DIR");
+    if (!d || !d[0]) return false;
+    arena.dir = d;
+    arena.path = arena_path(arena.dir, (int)getpid());
+    const int fd = open(arena.path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)ARENA_BYTES) != 0) { perror("cuda_emu: arena"); abort(); }
+    void *m = mmap(nullptr, ARENA_BYTES, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) { perror("cuda_emu: arena mmap"); abort(); }
+    arena.base = (unsigned char *)m;
+    arena.free_[0] = ARENA_BYTES;
+    atexit(arena_unlink);
+    return true;
+  }();
+  return on;
+}
+void *arena_alloc(size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  std::lock_guard<std::mutex> lk(arena.mu);
+  for (auto it = arena.free_.begin(); it != arena.free_.end(); ++it)
+    if (it->second >= bytes) {
+      const size_t off = it->first, left = it->second - bytes;
+      arena.free_.erase(it);
+      if (left) arena.free_[off + bytes] = left;
+      arena.used[off] = bytes;
+      return arena.base + off;
+    }
+  return nullptr;
+}
+bool arena_free(void *p) {
+  std::lock_guard<std::mutex> lk(arena.mu);
+  if (!arena.base || (unsigned char *)p < arena.base || (unsigned char *)p >= arena.base + ARENA_BYTES) return false;
+  const size_t off = (size_t)((unsigned char *)p - arena.base);
+  auto it = arena.used.find(off);
+  if (it == arena.used.end()) { fprintf(stderr, "cuda_emu: cudaFree of a pointer that is not an allocation\n"); abort(); }
+  size_t bytes = it->second, start = off;
+  arena.used.erase(it);
+  auto nx = arena.free_.find(start + bytes);  // coalesce with the free neighbours
+  if (nx != arena.free_.end()) { bytes += nx->second; arena.free_.erase(nx); }
+  auto pv = arena.free_.lower_bound(start);
+  if (pv != arena.free_.begin()) {
+    --pv;
+    if (pv->first + pv->second == start) { start = pv->first; bytes += pv->second; arena.free_.erase(pv); }
+  }
+  arena.free_[start] = bytes;
+  return true;
+}
+int device_count() {
+  static const int n = [] { const char *e = getenv("SPK_EMU_DEVICES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+  return n;
+}
+}  // namespace
+
+cudaError_t cudaGetDeviceCount(int *n) { *n = device_count(); return cudaSuccess; }
+cudaError_t cudaSetDevice(int dev) { return dev >= 0 && dev < device_count() ? cudaSuccess : cudaErrorInvalidValue; }
 cudaError_t emuMalloc(void **p, size_t bytes) {
   void *q = nullptr;
-  if (posix_memalign(&q, 256, bytes ? bytes : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  if (arena_enabled()) q = arena_alloc(bytes ? bytes : 1);
+  else if (posix_memalign(&q, 256, bytes ? bytes : 1) != 0) q = nullptr;
+  if (!q) { *p = nullptr; return cudaErrorMemoryAllocation; }
   memset(q, 0xCD, bytes);  // device memory is not initialised
   *p = q;
   return cudaSuccess;
 }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void *p) {
+  if (!p) return cudaSuccess;
+  if (arena_enabled() && arena_free(p)) return cudaSuccess;
+  free(p);
+  return cudaSuccess;
+}
 cudaError_t emuMallocHost(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
@@ -486,9 +624,43 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
   return cudaSuccess;
 }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+  if (!arena_enabled()) return cudaErrorNotSupported;
+  std::lock_guard<std::mutex> lk(arena.mu);
+  const size_t off = (size_t)((unsigned char *)p - arena.base);
+  auto it = arena.used.find(off);
+  if ((unsigned char *)p < arena.base || it == arena.used.end()) return cudaErrorInvalidValue;  // not the base of an allocation
+  IpcPayload pl = {IPC_MAGIC, (int32_t)getpid(), 0, off, it->second};
+  memset(h, 0, sizeof *h);
+  memcpy(h, &pl, sizeof pl);
+  return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+  if (!arena_enabled()) return cudaErrorNotSupported;
+  IpcPayload pl;
+  memcpy(&pl, &h, sizeof pl);
+  if (pl.magic != IPC_MAGIC) return cudaErrorInvalidValue;
+  if (pl.pid == (int32_t)getpid()) return cudaErrorInvalidValue;  // CUDA IPC cannot open a handle in the process that made it
+  std::lock_guard<std::mutex> lk(arena.mu);
+  auto it = arena.peers.find(pl.pid);
+  if (it == arena.peers.end()) {
+    const int fd = open(arena_path(arena.dir, pl.pid).c_str(), O_RDWR);
+    if (fd < 0) return cudaErrorInvalidValue;
+    void *m = mmap(nullptr, ARENA_BYTES, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return cudaErrorMemoryAllocation;
+    it = arena.peers.emplace(pl.pid, (unsigned char *)m).first;
+  }
+  *p = it->second + pl.offset;
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void *p) {
+  if (!arena_enabled()) return cudaErrorNotSupported;
+  std::lock_guard<std::mutex> lk(arena.mu);
+  for (const auto &kv : arena.peers)
+    if ((unsigned char *)p >= kv.second && (unsigned char *)p < kv.second + ARENA_BYTES) return cudaSuccess;  // mappings stay until exit
+  return cudaErrorInvalidValue;
+}
 cudaError_t cudaGetDriverEntryPoint(const char *symbol, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *status) {
   if (!strcmp(symbol, "cuTensorMapEncodeTiled")) {
     *fn = (void *)&emu::encode_tiled;

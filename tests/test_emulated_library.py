@@ -100,6 +100,48 @@ def test_plugin_scripts_pass_on_the_emulated_library(emu_lib):
     assert _run_gpu_tests(emu_lib, ["tests/test_plugin.py"]) >= 20
 
 
+MULTIRANK = [(2, "p2p", 29751), (2, "nccl", 29752), (4, "p2p", 29753)]
+
+
+@pytest.fixture(scope="module")
+def multirank_runs(emu_lib):
+    """the three multi-rank runs, started together (they mostly wait for each other's ranks)"""
+    import shutil
+    import tempfile
+    mod = _build_emu()
+    procs = []
+    for world, halo, port in MULTIRANK:
+        arena = tempfile.mkdtemp(prefix="spk_emu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        env = _env(emu_lib)
+        env.update(SPK_EMU_ARENA_DIR=arena, SPK_EMU_WORKERS="2", SPK_CUDA_NCCL_LIB=mod.NCCL_LIB, OMP_NUM_THREADS="1")
+        env.pop("SPK_CUDA_NO_P2P", None)
+        if halo == "nccl":
+            env["SPK_CUDA_NO_P2P"] = "1"
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+               "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "emu_mgpu_worker.py")]
+        procs.append((arena, subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    out = {}
+    for (world, halo, port), (arena, p) in zip(MULTIRANK, procs):
+        try:
+            out[(world, halo)] = p.communicate(timeout=1500)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out[(world, halo)] = p.communicate()
+        shutil.rmtree(arena, ignore_errors=True)
+    return out
+
+
+@pytest.mark.parametrize("world,halo", [(w, h) for w, h, _ in MULTIRANK])
+def test_slabs_on_several_ranks_equal_one_rank_on_the_emulated_library(multirank_runs, world, halo):
+    """The multi-GPU path, one process per rank: spparks_b200/selfcheck.py (the check tests/test_multigpu.py and
+    bench.py run on the GPUs: spins, counters, energy, cluster statistics of 8 app x lattice cases plus banded
+    lattices) with CUDA IPC emulated by shared file mappings — the neighbours' boundary stores and flag words go
+    through them — and NCCL by tests/host_shim/emu/nccl_emu.cpp.  4 ranks: lower and upper neighbour differ."""
+    stdout, stderr = multirank_runs[(world, halo)]
+    assert "MGPU_ALL_OK" in stdout, stdout[-3000:] + stderr[-3000:]
+    assert len(re.findall(r"^ok ", stdout, flags=re.M)) == 11, stdout
+
+
 TIER_SCRIPT = r"""
 import ctypes as C, json, os, sys
 import numpy as np
