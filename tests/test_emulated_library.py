@@ -100,6 +100,13 @@ def test_plugin_scripts_pass_on_the_emulated_library(emu_lib):
     assert _run_gpu_tests(emu_lib, ["tests/test_plugin.py"]) >= 20
 
 
+def test_smoke_passes_on_the_emulated_library(emu_lib):
+    """__graft_entry__.smoke(): the driver's one small invocation of the hot path, checked against the oracle"""
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke(); print('SMOKE_DONE')"], cwd=ROOT,
+                       env=_env(emu_lib), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SMOKE_DONE" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 MULTIRANK = [(2, "p2p", 29751), (2, "nccl", 29752), (4, "p2p", 29753)]
 
 
