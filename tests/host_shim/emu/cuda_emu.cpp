@@ -578,9 +578,47 @@ int device_count() {
 
 cudaError_t cudaGetDeviceCount(int *n) { *n = device_count(); return cudaSuccess; }
 cudaError_t cudaSetDevice(int dev) { return dev >= 0 && dev < device_count() ? cudaSuccess : cudaErrorInvalidValue; }
+// SPK_EMU_GUARD=after|before: every allocation gets an inaccessible page right behind its last
+// (16-byte rounded) byte, or right before its first one, so that a kernel reading or writing outside an
+// allocation faults at the access instead of silently using a neighbour's bytes (a memcheck for the CPU tier)
+namespace {
+struct Guarded { void *map; size_t map_bytes; };
+std::map<void *, Guarded> guarded;
+std::mutex guarded_mu;
+int guard_mode() {
+  static const int m = [] {
+    const char *e = getenv("SPK_EMU_GUARD");
+    return !e ? 0 : !strcmp(e, "after") ? 1 : !strcmp(e, "before") ? 2 : 0;
+  }();
+  return m;
+}
+void *guarded_alloc(size_t bytes) {
+  const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  const size_t body = (need + page - 1) / page * page;
+  unsigned char *m = (unsigned char *)mmap(nullptr, body + 2 * page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (m == MAP_FAILED) return nullptr;
+  mprotect(m, page, PROT_NONE);
+  mprotect(m + page + body, page, PROT_NONE);
+  void *p = guard_mode() == 1 ? m + page + body - need : m + page;
+  std::lock_guard<std::mutex> lk(guarded_mu);
+  guarded[p] = Guarded{m, body + 2 * page};
+  return p;
+}
+bool guarded_free(void *p) {
+  std::lock_guard<std::mutex> lk(guarded_mu);
+  auto it = guarded.find(p);
+  if (it == guarded.end()) return false;
+  munmap(it->second.map, it->second.map_bytes);
+  guarded.erase(it);
+  return true;
+}
+}  // namespace
+
 cudaError_t emuMalloc(void **p, size_t bytes) {
   void *q = nullptr;
   if (arena_enabled()) q = arena_alloc(bytes ? bytes : 1);
+  else if (guard_mode()) q = guarded_alloc(bytes ? bytes : 1);
   else if (posix_memalign(&q, 256, bytes ? bytes : 1) != 0) q = nullptr;
   if (!q) { *p = nullptr; return cudaErrorMemoryAllocation; }
   memset(q, 0xCD, bytes);  // device memory is not initialised
@@ -590,6 +628,10 @@ cudaError_t emuMalloc(void **p, size_t bytes) {
 cudaError_t cudaFree(void *p) {
   if (!p) return cudaSuccess;
   if (arena_enabled() && arena_free(p)) return cudaSuccess;
+  if (guard_mode()) {
+    if (!guarded_free(p)) { fprintf(stderr, "cuda_emu: cudaFree of a pointer that is not an allocation\n"); abort(); }
+    return cudaSuccess;
+  }
   free(p);
   return cudaSuccess;
 }
@@ -759,6 +801,14 @@ int spk_emu_selftest(void) {
   if (__funnelshift_l(0x80000000u, 0x00000001u, 1) != 0x00000003u || __funnelshift_r(0x00000003u, 0x00000001u, 1) != 0x80000001u)
     return 11;
   return 0;
+}
+// reads one byte at `offset` of a fresh 100-byte allocation (the test of SPK_EMU_GUARD: outside -> fault)
+int spk_emu_guard_probe(long offset) {
+  unsigned char *p = nullptr;
+  if (cudaMalloc(&p, 100) != cudaSuccess) return -1;
+  const int v = *(volatile unsigned char *)(p + offset);
+  cudaFree(p);
+  return v;
 }
 void spk_emu_launch_log_reset(void) {
   std::lock_guard<std::mutex> lk(emu::pool.mu);

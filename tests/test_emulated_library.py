@@ -71,6 +71,30 @@ def test_emulator_selftest(emu_lib):
     assert L.spk_emu_selftest() == 0
 
 
+@pytest.mark.parametrize("guard,inside,outside", [("after", 99, 112), ("before", 0, -1)])
+def test_guard_pages_fault_on_accesses_outside_an_allocation(emu_lib, guard, inside, outside):
+    """SPK_EMU_GUARD: the memcheck of the CPU tier really faults (112 = the first byte past the 16-byte rounded end)"""
+    code = "import ctypes as C, sys; L = C.CDLL(%r); L.spk_emu_guard_probe.argtypes = [C.c_long]; print(L.spk_emu_guard_probe(int(sys.argv[1])))"
+    env = dict(os.environ, SPK_EMU_GUARD=guard)
+    ok = subprocess.run([sys.executable, "-c", code % emu_lib, str(inside)], env=env, capture_output=True, text=True, timeout=120)
+    assert ok.returncode == 0 and ok.stdout.strip() == str(0xCD), ok.stdout + ok.stderr
+    bad = subprocess.run([sys.executable, "-c", code % emu_lib, str(outside)], env=env, capture_output=True, text=True, timeout=120)
+    assert bad.returncode == -11, (bad.returncode, bad.stdout, bad.stderr)
+
+
+def test_gpu_parity_tests_with_guard_pages(emu_lib):
+    """a slice of the parity tests (shadows interleaved with int32 calls, masks, several-tile lattices, ...) with an inaccessible page behind
+    every device allocation: no kernel reads or writes past the end of the lattice, its ghost layers, the shadows"""
+    env_guard = dict(os.environ)
+    os.environ["SPK_EMU_GUARD"] = "after"
+    try:
+        n = _run_gpu_tests(emu_lib, ["tests/test_gpu_parity.py", "-k", "interleaved or masked or large_lattices or extreme or elimination or nloop or edge_sizes or per_colour"])
+    finally:
+        os.environ.clear()
+        os.environ.update(env_guard)
+    assert n >= 30
+
+
 def test_product_loader_refuses_the_emulated_build(emu_lib):
     code = ("import spparks_b200._lib as l\n"
             "try:\n    l.load()\nexcept l.SpkCudaError as e:\n    print('REFUSED', e)\nelse:\n    print('LOADED')\n")
@@ -127,7 +151,15 @@ def multirank_runs(emu_lib):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
                "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "emu_mgpu_worker.py")]
         procs.append((arena, subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    # next to them: a slice of the randomised multi-rank test at 3 ranks (tools/emu_fuzz_ranks.py)
+    fuzz = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "emu_fuzz_ranks.py"), "--ranks", "3", "--cases", "12", "--seed", "21",
+                             "--port", "29754"], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     out = {}
+    try:
+        out["fuzz3"] = fuzz.communicate(timeout=1500) + (fuzz.returncode,)
+    except subprocess.TimeoutExpired:
+        fuzz.kill()
+        out["fuzz3"] = fuzz.communicate() + (-9,)
     for (world, halo, port), (arena, p) in zip(MULTIRANK, procs):
         try:
             out[(world, halo)] = p.communicate(timeout=1500)
@@ -147,6 +179,21 @@ def test_slabs_on_several_ranks_equal_one_rank_on_the_emulated_library(multirank
     stdout, stderr = multirank_runs[(world, halo)]
     assert "MGPU_ALL_OK" in stdout, stdout[-3000:] + stderr[-3000:]
     assert len(re.findall(r"^ok ", stdout, flags=re.M)) == 11, stdout
+
+
+def test_random_cases_on_three_ranks(multirank_runs):
+    """tools/emu_fuzz_ranks.py: random app / lattice / extents / tier / halo mode / call pattern, slabs gathered and
+    compared with the oracle (spins, counters, energy, cluster statistics); a fixed seed here, thousands of cases by hand"""
+    stdout, stderr, rc = multirank_runs["fuzz3"]
+    assert rc == 0 and "3 ranks: 12 / 12 cases ok" in stdout, stdout[-3000:] + stderr[-2000:]
+
+
+def test_random_cases_on_one_rank(emu_lib):
+    """tools/emu_fuzz.py: random app / lattice / tile-edge extents / Q / T / kernel tier / sweeps, colour calls with
+    nloop, sector sets, masked sector sets, against the oracle"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emu_fuzz.py"), "--cases", "80", "--seed", "11"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "80 / 80 cases, 0 failures" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 TIER_SCRIPT = r"""
