@@ -131,7 +131,14 @@ def test_smoke_passes_on_the_emulated_library(emu_lib):
     assert r.returncode == 0 and "SMOKE_DONE" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-MULTIRANK = [(2, "p2p", 29751), (2, "nccl", 29752), (4, "p2p", 29753)]
+MULTIRANK = [(2, "p2p"), (2, "nccl"), (4, "p2p")]
+
+
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
 
 
 @pytest.fixture(scope="module")
@@ -141,7 +148,7 @@ def multirank_runs(emu_lib):
     import tempfile
     mod = _build_emu()
     procs = []
-    for world, halo, port in MULTIRANK:
+    for world, halo in MULTIRANK:
         arena = tempfile.mkdtemp(prefix="spk_emu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         env = _env(emu_lib)
         env.update(SPK_EMU_ARENA_DIR=arena, SPK_EMU_WORKERS="2", SPK_CUDA_NCCL_LIB=mod.NCCL_LIB, OMP_NUM_THREADS="1")
@@ -149,18 +156,18 @@ def multirank_runs(emu_lib):
         if halo == "nccl":
             env["SPK_CUDA_NO_P2P"] = "1"
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
-               "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "emu_mgpu_worker.py")]
+               "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "emu_mgpu_worker.py")]
         procs.append((arena, subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
     # next to them: a slice of the randomised multi-rank test at 3 ranks (tools/emu_fuzz_ranks.py)
     fuzz = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "emu_fuzz_ranks.py"), "--ranks", "3", "--cases", "12", "--seed", "21",
-                             "--port", "29754"], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                             "--port", str(_free_port())], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     out = {}
     try:
         out["fuzz3"] = fuzz.communicate(timeout=1500) + (fuzz.returncode,)
     except subprocess.TimeoutExpired:
         fuzz.kill()
         out["fuzz3"] = fuzz.communicate() + (-9,)
-    for (world, halo, port), (arena, p) in zip(MULTIRANK, procs):
+    for (world, halo), (arena, p) in zip(MULTIRANK, procs):
         try:
             out[(world, halo)] = p.communicate(timeout=1500)
         except subprocess.TimeoutExpired:
@@ -170,7 +177,7 @@ def multirank_runs(emu_lib):
     return out
 
 
-@pytest.mark.parametrize("world,halo", [(w, h) for w, h, _ in MULTIRANK])
+@pytest.mark.parametrize("world,halo", MULTIRANK)
 def test_slabs_on_several_ranks_equal_one_rank_on_the_emulated_library(multirank_runs, world, halo):
     """The multi-GPU path, one process per rank: spparks_b200/selfcheck.py (the check tests/test_multigpu.py and
     bench.py run on the GPUs: spins, counters, energy, cluster statistics of 8 app x lattice cases plus banded
