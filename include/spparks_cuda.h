@@ -89,6 +89,16 @@ int spk_cuda_site_energy(spk_cuda_handle *h, unsigned char *host, int64_t n);
  * src/app_potts_pin.cpp:262-283; NOT the reference's random stream) */
 int spk_cuda_randomize(spk_cuda_handle *h, uint64_t seed, int32_t lo, int32_t hi);
 int spk_cuda_pin_random(spk_cuda_handle *h, uint64_t seed, double fraction);
+/* `pin fraction multi nthresh` of app_style potts/pin ON THE DEVICE, bit for bit the reference's
+ * pinned sites (AppPottsPin::pin_create, src/app_potts_pin.cpp:242-349): park_seed is the state of
+ * `new RandomPark(ranmaster->uniform())` (:248), as for spk_cuda_set_site_range.  multi = 0, nthresh = 0
+ * (pins anywhere; the attempts of a round commute) runs in parallel and on any number of ranks
+ * (collective; after spk_cuda_comm_init); multi = 1 or nthresh > 0 depend on the order of the attempts and
+ * are walked by one device thread in the reference's order (one GPU, one-shot).  *npinned = pinned sites
+ * of the lattice afterwards.  Where the reference would loop forever (no site can be pinned any more) an
+ * error is returned instead.  Lattices beyond 2^31 sites: the reference's 32-bit tagint cannot address
+ * them; the same formula is evaluated in 64 bits. */
+int spk_cuda_pin_create(spk_cuda_handle *h, double fraction, int multi, int nthresh, int32_t park_seed, int64_t *npinned);
 
 /* One colour set = one kernel: replaces (this->*sweep)(set.nlocal,set.site2i) x nloop
  * (src/app_lattice.cpp:674-691) for the set {sites of `color` inside `box`}.

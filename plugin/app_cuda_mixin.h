@@ -110,6 +110,36 @@ class AppCudaMixin : public Base, public SpkCudaHost {
         if (this->screen) fprintf(this->screen,"  " BIGINT_FORMAT " settings made for site\n",allcount);
         if (this->logfile) fprintf(this->logfile,"  " BIGINT_FORMAT " settings made for site\n",allcount);
       }
+    } else if (strcmp(command,"cuda_pin") == 0) {
+      // cuda_pin fraction multi nthresh  ==  pin fraction multi nthresh of app_style potts/pin
+      // (src/app_potts_pin.cpp:52-65, 242-349) computed on the device: same draw from the master
+      // generator, same pinned sites.  multi = 1 and nthresh > 0 depend on the order of the attempts:
+      // one rank only (the library says so)
+      if (narg != 3) this->error->all(FLERR,"Illegal pin command");
+      if (this->sites_exist == 0) this->error->all(FLERR,"Pin command before sites exist");
+      double pfrac = atof(arg[0]);
+      int pmulti = atoi(arg[1]), pthresh = atoi(arg[2]);
+      if (pfrac < 0.0 || pfrac > 1.0 || (pmulti != 0 && pmulti != 1) || pthresh < 0)
+        this->error->all(FLERR,"Illegal pin command");
+      int pseed = static_cast<int> (this->ranmaster->uniform()*2147483647);   // new RandomPark(double), :248
+      if (pseed == 0) pseed = 1;
+      spk_cuda_handle *tmp = NULL;
+      spk_cuda_desc desc;
+      fill_desc(desc,0.0);
+      check(spk_cuda_create(&desc,&tmp));
+      int rc = 0;
+      if (this->nprocs > 1) {
+        char id[SPK_CUDA_COMM_ID_BYTES];
+        if (this->me == 0) rc = spk_cuda_comm_id(id);
+        MPI_Bcast(id,SPK_CUDA_COMM_ID_BYTES,MPI_CHAR,0,this->world);
+        if (!rc) rc = spk_cuda_comm_init(tmp,id);
+      }
+      int64_t npinned = 0;
+      if (!rc) rc = spk_cuda_upload_spins(tmp,this->iarray[0],this->nlocal);
+      if (!rc) rc = spk_cuda_pin_create(tmp,pfrac,pmulti,pthresh,pseed,&npinned);
+      if (!rc) rc = spk_cuda_download_spins(tmp,this->iarray[0],this->nlocal);
+      spk_cuda_destroy(tmp);
+      check(rc);
     } else if (strcmp(command,"cuda_host_sync") == 0) {
       // yes (default): iarray[0] is refreshed before every Output::compute, as host-side
       //   diagnostics and dumps expect

@@ -27,7 +27,7 @@ SYMBOLS = [
     "spk_cuda_cluster_ids", "spk_cuda_neigh_variant", "spk_cuda_timer_lap", "spk_cuda_timer_laps",
     "spk_cuda_digest", "spk_cuda_mask_enable", "spk_cuda_mask_clear_border", "spk_cuda_download_mask",
     "spk_cuda_host_register", "spk_cuda_host_unregister", "spk_cuda_set_site_range", "spk_cuda_site_energy",
-    "spk_cuda_sweep_path",
+    "spk_cuda_sweep_path", "spk_cuda_pin_create",
 ]
 
 
@@ -74,6 +74,7 @@ def load():
     L.spk_cuda_set_temperature.argtypes = [vp, C.c_double]
     L.spk_cuda_randomize.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32]
     L.spk_cuda_pin_random.argtypes = [vp, C.c_uint64, C.c_double]
+    L.spk_cuda_pin_create.argtypes = [vp, C.c_double, C.c_int, C.c_int, C.c_int32, i64p]
     L.spk_cuda_sweep_color.argtypes = [vp, C.c_uint32, C.c_int, i32p, C.c_int]
     L.spk_cuda_sweep_color_injected.argtypes = [vp, C.c_int, i32p, dp, dp]
     L.spk_cuda_set_siteseeds.argtypes = [vp, vp, C.c_int64]

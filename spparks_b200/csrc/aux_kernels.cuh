@@ -66,6 +66,97 @@ __global__ void pin_kernel(int32_t *spin, long long n, long long goff, unsigned 
   }
 }
 
+// `pin fraction 0 0` of app_style potts/pin, bit for bit (src/app_potts_pin.cpp:262-283, multi = 0,
+// nthresh = 0): every attempt draws a global site id from ONE Park-Miller stream
+// (tagrandom: (tagint)(uniform()*nglobal) + 1, src/random_park.cpp:103-108) and pins it; pinning is
+// idempotent, so the attempts of a round commute and draw number d of the stream (0-based over
+// the whole command) is evaluated on its own with a modular power, like set_range_kernel.  Every
+// rank walks the same draws and keeps the ids that fall into its slab.
+__global__ void __launch_bounds__(256) pin_draws_kernel(int32_t *spin, long long n, long long goff, uint32_t seed0,
+                                                        unsigned long long first_draw, long long ndraws, long long nglobal,
+                                                        int pinned) {
+  const uint32_t step32 = pm_powmod(16807u, 32ull);
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long per = ((ndraws + 31) / 32 + nwarps - 1) / nwarps * 32;  // draws per warp, multiple of 32
+  const long long first = warp * per, last = first + per < ndraws ? first + per : ndraws;
+  if (first >= ndraws) return;
+  uint32_t state = pm_mulmod(seed0, pm_powmod(16807u, first_draw + (unsigned long long)(first + lane) + 1ull));
+  for (long long d = first + lane; d < last; d += 32) {
+    const double u = (1.0 / 2147483647) * (double)(int)state;  // RandomPark::uniform: AM*seed
+    long long id = (long long)(u * (double)nglobal) + 1;      // tagrandom
+    if (id > nglobal) id = nglobal;
+    const long long s = id - 1 - goff;
+    if (s >= 0 && s < n) spin[s] = pinned;
+    state = pm_mulmod(state, step32);
+  }
+}
+
+// The pin modes whose attempts do NOT commute — nthresh > 0 (a site is pinned only if at least
+// nthresh neighbours differ from it, and an earlier pin of the same round changes that count,
+// src/app_potts_pin.cpp:268-274) and multi = 1 (a site and all its neighbours, only where none of
+// them is pinned yet, :291-335) — walked by ONE thread in the reference's order: exact, one-shot,
+// slow by construction (a dependent chain of random accesses).  One GPU only.
+// out[0] = pinned sites added, out[1] = draws consumed, out[2] = 1 if the draw budget ran out
+// (multi: no site satisfies the conditions any more; the reference would loop forever).
+template <int LAT>
+__global__ void pin_sequential_kernel(int32_t *spin, Geo g, uint32_t seed0, unsigned long long first_draw, long long ndraws,
+                                      long long ndesired, long long already, int multi, int nthresh, int Q,
+                                      unsigned long long *out) {
+  using L = Lat<LAT>;
+  constexpr int NN = L::NN, NB = L::NB;
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const long long nglobal = (long long)g.X * g.Y * g.Z * NB;
+  const long long sy = (long long)g.X * NB, sz = sy * g.Y;
+  uint32_t state = pm_mulmod(seed0, pm_powmod(16807u, first_draw));
+  long long added = 0, draws = 0, npin = 0;  // npin: the reference's variable (multi: 0 until the first insertion)
+  bool exhausted = false;
+  // multi = 0: exactly ndraws attempts (one round, the host recounts between rounds); multi = 1: until npin >= ndesired
+  while (multi ? npin < ndesired : draws < ndraws) {
+    if (multi && draws >= ndraws) { exhausted = true; break; }
+    state = pm_mulmod(state, 16807u);
+    draws++;
+    const double u = (1.0 / 2147483647) * (double)(int)state;
+    long long id = (long long)(u * (double)nglobal) + 1;
+    if (id > nglobal) id = nglobal;
+    const long long s = id - 1;
+    const int m = (int)(s % NB);
+    const long long cell = s / NB;
+    const int i = (int)(cell % g.X), j = (int)((cell / g.X) % g.Y), k = (int)(cell / ((long long)g.X * g.Y));
+    long long nb[NN];
+#pragma unroll
+    for (int n = 0; n < NN; n++) {
+      const Off o = L::off(m, n);
+      int ii = i + o.dx, jj = j + o.dy, kk = k + o.dz;
+      ii = ii < 0 ? ii + g.X : (ii >= g.X ? ii - g.X : ii);
+      jj = jj < 0 ? jj + g.Y : (jj >= g.Y ? jj - g.Y : jj);
+      kk = kk < 0 ? kk + g.Z : (kk >= g.Z ? kk - g.Z : kk);
+      nb[n] = kk * sz + jj * sy + (long long)ii * NB + o.m;
+    }
+    const int me = spin[s];
+    int ndiff = 0;
+    bool free_ = me <= Q;
+    for (int n = 0; n < NN; n++) {
+      const int v = spin[nb[n]];
+      ndiff += v != me;
+      free_ = free_ && v <= Q;
+    }
+    if (!multi) {
+      if (ndiff >= nthresh && me <= Q) added++;
+      if (ndiff >= nthresh) spin[s] = Q + 1;
+    } else if (free_ && (nthresh == 0 || ndiff >= nthresh)) {
+      spin[s] = Q + 1;
+      added++;
+      for (int n = 0; n < NN; n++)
+        if (spin[nb[n]] <= Q) { spin[nb[n]] = Q + 1; added++; }  // (periodic images on tiny lattices repeat a neighbour)
+      npin = already + added;
+    }
+  }
+  out[0] = (unsigned long long)added;
+  out[1] = (unsigned long long)draws;
+  out[2] = exhausted ? 1ull : 0ull;
+}
+
 // init_app's spin check (src/app_potts.cpp:83-90, src/app_ising.cpp:74-81, src/app_potts_pin.cpp:78-84):
 // number of sites whose value lies outside [lo, hi]
 __global__ void __launch_bounds__(256) validate_kernel(const int32_t *__restrict__ spin, long long n, int lo, int hi,

@@ -734,6 +734,92 @@ int spk_cuda_pin_random(spk_cuda_handle *h, uint64_t seed, double fraction) {
   return 0;
 }
 
+// number of pinned sites (spin > Q) of the whole lattice: the reference's recount after every round
+// of pin_create (src/app_potts_pin.cpp:279-282: local count + MPI_Allreduce)
+static int count_pinned(spk_cuda_handle *h, long long *npin) {
+  CU(cudaMemsetAsync(h->escratch, 0, sizeof(unsigned long long), h->stream));
+  validate_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, -2147483647 - 1, h->d.nspins, h->escratch);
+  h->launches++;
+  CU(cudaGetLastError());
+  if (h->d.nranks > 1) NC(g_nccl.AllReduce(h->escratch, h->escratch, 1, ncclUint64, ncclSum, h->comm, h->stream));
+  unsigned long long c = 0;
+  CU(cudaMemcpyAsync(&c, h->escratch, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *npin = (long long)c;
+  return 0;
+}
+
+int spk_cuda_pin_create(spk_cuda_handle *h, double fraction, int multi, int nthresh, int32_t park_seed, int64_t *npinned) {
+  if (!h) return fail("null handle");
+  if (h->d.model != SPK_POTTS_PIN) return fail("pin is only defined for app_style potts/pin");
+  if (fraction < 0.0 || fraction > 1.0 || (multi != 0 && multi != 1) || nthresh < 0) return fail("Illegal pin command");
+  if (park_seed < 1 || park_seed >= 2147483647) return fail("Park-Miller seed must lie in [1, 2^31-2]");
+  if (h->d.nranks > 1 && !h->comm) return fail("pin on several ranks needs spk_cuda_comm_init first");
+  const bool commuting = multi == 0 && nthresh == 0;
+  if (!commuting && h->d.nranks > 1)
+    return fail("pin with multi = 1 or nthresh > 0 depends on the order of the attempts: one GPU only (nranks must be 1)");
+  CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, true)) return 1;
+  const long long ndesired = (long long)(fraction * (double)h->nglobal);  // static_cast<int>(pfraction*nglobal), :246
+  const long long goff = (long long)h->g.g0 * h->plane;
+  const int Q = h->d.nspins;
+  unsigned long long draw = 0;  // draws of the command's stream consumed so far
+  long long npin = 0;           // the reference's npin: 0 until the first recount, whatever was pinned before
+  unsigned long long *out = nullptr;
+  if (!commuting) CU(cudaMalloc(&out, 3 * sizeof(unsigned long long)));
+  auto sequential = [&](long long ndraws, long long already, unsigned long long (&res)[3]) -> int {
+    switch (h->d.lattice) {
+#define SPK_PIN(LATV) case LATV: pin_sequential_kernel<LATV><<<1, 32, 0, h->stream>>>(h->spin, h->g, (uint32_t)park_seed, draw, ndraws, ndesired, already, multi, nthresh, Q, out); break;
+      SPK_PIN(SPK_SQ_4N) SPK_PIN(SPK_SQ_8N) SPK_PIN(SPK_TRI) SPK_PIN(SPK_SC_6N) SPK_PIN(SPK_SC_26N)
+#undef SPK_PIN
+      default: return fail("unknown lattice %d", h->d.lattice);
+    }
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(res, out, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+  };
+  int rc = 0, stalled = 0;
+  if (!multi) {
+    while (rc == 0 && npin < ndesired) {  // rounds of ndesired - npin attempts, recount after each (:262-283)
+      const long long nattempt = ndesired - npin;
+      if (commuting) {
+        pin_draws_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, h->nlocal, goff, (uint32_t)park_seed, draw, nattempt, h->nglobal, Q + 1);
+        h->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail("pin: kernel launch failed");
+      } else {
+        unsigned long long res[3];
+        rc = sequential(nattempt, 0, res);
+      }
+      draw += (unsigned long long)nattempt;
+      const long long before = npin;
+      if (rc == 0) rc = count_pinned(h, &npin);
+      // the reference would loop forever when no site can be pinned any more (nthresh too high)
+      stalled = npin == before ? stalled + 1 : 0;
+      if (rc == 0 && stalled >= 64) rc = fail("pin: %lld of %lld sites pinned and no attempt of the last 64 rounds succeeded", npin, ndesired);
+    }
+  } else {
+    long long already = 0;
+    rc = count_pinned(h, &already);
+    if (rc == 0 && ndesired > 0) {
+      unsigned long long res[3];
+      const long long budget = 64 * (long long)h->nglobal + 1000000;  // draws; far beyond what a satisfiable request needs
+      rc = sequential(budget, already, res);
+      if (rc == 0 && res[2]) rc = fail("pin: no site left whose neighbourhood is free of pinned sites (%llu pinned, %lld wanted)",
+                                       (unsigned long long)already + res[0], ndesired);
+      npin = already + (long long)res[0];
+    } else {
+      npin = already;
+    }
+  }
+  cudaFree(out);
+  h->ghosts_valid = false;
+  if (rc) return rc;
+  if (npinned) *npinned = npin;
+  return 0;
+}
+
 int spk_cuda_sweep_color(spk_cuda_handle *h, uint32_t sweep, int color, const int32_t *box, int nloop) {
   if (!h) return fail("null handle");
   h->ev.sweep = sweep;

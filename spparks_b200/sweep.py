@@ -83,6 +83,12 @@ class LatticeSweep:
     def pin_random(self, seed, fraction):
         _lib.check(self.L.spk_cuda_pin_random(self.h, seed, fraction))
 
+    def pin_create(self, park_seed, fraction, multi=0, nthresh=0):
+        """`pin fraction multi nthresh` with the reference's own stream; returns the pinned sites of the lattice"""
+        n = C.c_int64()
+        _lib.check(self.L.spk_cuda_pin_create(self.h, fraction, multi, nthresh, park_seed, C.byref(n)))
+        return n.value
+
     def set_temperature(self, t):
         _lib.check(self.L.spk_cuda_set_temperature(self.h, t))
 

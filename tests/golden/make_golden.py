@@ -234,9 +234,39 @@ def main_variants():
     gen_strict("potts/neigh", 5, "tri", (8, 8, 1), 0.4, 6, rng)
 
 
+def gen_pins(lattice, n, q, fraction, multi, nthresh, seed, rng, blocky):
+    """`pin fraction multi nthresh` of app_style potts/pin (src/app_potts_pin.cpp:216-349) run by the
+    reference itself: spins before and after.  The lattice is loaded (blocky = grains, so that nthresh > 0
+    finds boundaries), the master stream has served `set site range` once before the pin command."""
+    ns = nsites(lattice, n)
+    s0 = random_spins(rng, "potts/pin", q, ns, blocky=blocky)
+    with tempfile.TemporaryDirectory() as tmp:
+        s0.tofile(os.path.join(tmp, "s0.bin"))
+        lines = header("potts/pin", q, lattice, n, seed=seed) + ["@load s0.bin", "pin %r %d %d" % (fraction, multi, nthresh),
+                                                                 "@save s1.bin"]
+        run_driver(lines, tmp)
+        s1 = ints(tmp, "s1.bin")
+    name = "pins_%s_m%d_t%d.npz" % (tag(lattice), multi, nthresh)
+    np.savez_compressed(os.path.join(HERE, name), s0=s0, s1=s1, n=np.array(n), q=q, fraction=fraction, multi=multi,
+                        nthresh=nthresh, seed=seed, lattice=lattice)
+    print(name, "pinned", int((s1 > q).sum()), "of", ns)
+
+
+def main_pins():
+    rng = np.random.default_rng(20261017)
+    gen_pins("sc/26n", (12, 10, 8), 50, 0.05, 0, 0, 4711, rng, False)
+    gen_pins("sq/8n", (40, 30, 1), 9, 0.3, 0, 0, 99, rng, False)      # many rounds: most picks hit pinned sites
+    gen_pins("tri", (16, 12, 1), 20, 0.1, 0, 0, 31337, rng, False)
+    gen_pins("sc/26n", (12, 10, 8), 6, 0.04, 0, 10, 4711, rng, True)   # only at grain boundaries
+    gen_pins("sq/4n", (30, 30, 1), 5, 0.1, 1, 0, 777, rng, False)      # site + its neighbours
+    gen_pins("sc/6n", (10, 10, 10), 5, 0.15, 1, 2, 555, rng, True)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         main_variants()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pins":
+        main_pins()
     elif len(sys.argv) > 1 and sys.argv[1] == "mask":
         main_mask()
     else:

@@ -116,6 +116,12 @@ def test_cluster_tests_pass_on_the_emulated_library(emu_lib):
     assert _run_gpu_tests(emu_lib, ["tests/test_cluster.py", "-k", "not large"]) >= 12
 
 
+def test_device_pin_tests_pass_on_the_emulated_library(emu_lib):
+    """device-side `pin f multi nthresh` against the reference's pinned sites (fixtures), the oracle, and through
+    the plugin's `cuda_pin` against the reference binary's `pin`"""
+    assert _run_gpu_tests(emu_lib, ["tests/test_zz_device_pin.py"]) >= (20 if os.path.exists(SPK_CUDA) else 17)
+
+
 @pytest.mark.skipif(not os.path.exists(SPK_CUDA), reason="plugin/_build/spk_cuda not built (needs the reference tree)")
 def test_plugin_scripts_pass_on_the_emulated_library(emu_lib):
     """the SPPARKS binary with the app-style plugin runs its in.* scripts against the emulated library"""

@@ -217,3 +217,18 @@ def test_golden_log_in_potts_full():
     o = O.Oracle("potts", "sc/26n", 20, 20, 20, 100, 0.0)
     spin = o.set_site_range(1, 100, m)
     _check_rows(o.run_sweep_random(spin, m, True, 10.0, 100.0), POTTS_LOG)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "pins_*.npz"))), ids=os.path.basename)
+def test_oracle_pin_create_equals_the_reference(path):
+    """AppPottsPin::pin_create run by the reference (`pin fraction multi nthresh` after `set site range`,
+    spins loaded in between): single sites anywhere, at grain boundaries only, site + neighbours"""
+    d = np.load(path)
+    n, q = [int(x) for x in d["n"]], int(d["q"])
+    o = O.Oracle("potts/pin", str(d["lattice"]), n[0], n[1], n[2], q, 0.5)
+    m = O.mars(int(d["seed"]))
+    o.set_site_range(1, q, m)  # the master generator's first draw went to `set site range`
+    s = d["s0"].copy()
+    npin = o.pin_create(s, float(d["fraction"]), int(d["multi"]), int(d["nthresh"]), m)
+    assert np.array_equal(s, d["s1"])
+    assert npin == int((d["s1"] > q).sum())

@@ -51,7 +51,9 @@ def draw_case(rng, world):
             "halo": str(rng.choice(["p2p", "p2p", "nccl"])), "seed": int(rng.integers(1, 2**40)),
             "calls": [int(x) for x in rng.integers(1, 4, size=int(rng.integers(1, 4)))],   # sweeps per spk_cuda_sweeps call
             "between": [str(x) for x in rng.choice(["none", "energy", "clusters", "download"], size=3)],
-            "start": str(rng.choice(["random", "few", "grains"]))}
+            "start": str(rng.choice(["random", "few", "grains"])),
+            # potts/pin: half of the cases get their pins from the device-side `pin f 0 0` (collective) instead of the upload
+            "pin": float(rng.choice([0.0, 0.0, 0.02, 0.3]))}
 
 
 def worker(cases):
@@ -81,7 +83,8 @@ def worker(cases):
             idx = np.arange(o.nsites) // o.nbasis
             i, j, k = idx % n[0], (idx // n[0]) % n[1], idx // (n[0] * n[1])
             spins = (1 + ((i // 5) * 7 + (j // 3) * 13 + (k // 2) * 29) % top).astype(np.int32)
-        if model == "potts/pin":
+        device_pin = model == "potts/pin" and c.get("pin", 0.0) > 0
+        if model == "potts/pin" and not device_pin:
             spins[rng.random(o.nsites) < 0.07] = q + 1
         what = None
         try:
@@ -93,6 +96,13 @@ def worker(cases):
             s.comm_init(idt.numpy().tobytes())
             s.upload(spins[rank * s.nlocal:(rank + 1) * s.nlocal])
             want = spins.copy()
+            if device_pin:
+                m = O.mars(c["seed"] % 900000000 + 1)
+                park = int(O.lib().orc_mars_uniform(O.C.byref(m)) * O.IM) or 1
+                npin = s.pin_create(park, c["pin"])
+                onpin = o.pin_create(want, c["pin"], 0, 0, O.mars(c["seed"] % 900000000 + 1))
+                if npin != onpin:
+                    what = "pin_create: %d sites pinned, oracle %d" % (npin, onpin)
             nacc, sweep = 0, 7
             energies, clusters = [], []
             for ci, ns in enumerate(c["calls"]):
@@ -117,7 +127,9 @@ def worker(cases):
             s.close()
             if rank == 0:
                 got = torch.cat(parts).numpy()
-                if not np.array_equal(got, want):
+                if what is not None:
+                    pass
+                elif not np.array_equal(got, want):
                     bad = np.flatnonzero(got != want)
                     what = "spins differ at %d sites, first %d" % (bad.size, int(bad[0]))
                 elif (int(acc[0]), int(acc[1])) != (nacc, sum(c["calls"]) * o.nsites):
