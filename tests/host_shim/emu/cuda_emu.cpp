@@ -85,6 +85,34 @@ struct Context {
 inline void switch_context(Context &from, Context &to) { swapcontext(&from.uc, &to.uc); }
 #endif
 
+struct PendingCopy {
+  unsigned char *dst;
+  unsigned char desc[128];
+  int coord[5];
+  int rank;
+  uint64_t *bar;
+  uint64_t bytes;
+};
+int order_mode() {
+  static const int m = [] {
+    const char *e = getenv("SPK_EMU_ORDER");
+    return !e ? 0 : !strncmp(e, "reverse", 7) ? 1 : !strncmp(e, "shuffle", 7) ? 2 : 0;
+  }();
+  return m;
+}
+uint64_t order_seed() {
+  static const uint64_t sd = [] {
+    const char *e = getenv("SPK_EMU_ORDER");
+    const char *c = e ? strchr(e, ':') : nullptr;
+    return c ? strtoull(c + 1, nullptr, 10) : 12345ull;
+  }();
+  return sd;
+}
+bool tma_lazy() {
+  static const bool on = [] { const char *e = getenv("SPK_EMU_TMA"); return e && !strcmp(e, "lazy"); }();
+  return on;
+}
+
 struct Fiber {
   Context ctx;
   Tls tls;
@@ -107,6 +135,8 @@ struct Worker {
   long stalled = 0;
   unsigned char *smem = nullptr;
   const std::function<void()> *body = nullptr;
+  std::vector<int> perm;                 // fiber slot -> CUDA thread index
+  std::vector<struct PendingCopy> pending;  // SPK_EMU_TMA=lazy: bulk tensor copies issued and not yet performed
 };
 thread_local Worker *W = nullptr;
 
@@ -192,8 +222,21 @@ void run_cta(Worker *w, dim3 block, dim3 bid, const std::function<void()> *body)
     ws.lanes = ws.alive = std::min(32, n - 32 * q);
     ws.count = 0;
   }
-  for (int i = 0; i < n; i++) {
-    Fiber &f = w->fibers[(size_t)i];
+  // SPK_EMU_ORDER=reverse|shuffle[:seed]: which CUDA thread runs first inside a CTA (fibers only switch at the
+  // blocking points, so the order decides who gets to a shared-memory location first between two barriers: a
+  // kernel that misses a barrier computes different results under a different order)
+  w->perm.resize((size_t)n);
+  for (int i = 0; i < n; i++) w->perm[(size_t)i] = order_mode() == 1 ? n - 1 - i : i;
+  if (order_mode() == 2) {
+    uint64_t x = order_seed() ^ (0x9E3779B97F4A7C15ull * (uint64_t)(1 + bid.x + 7919u * bid.y + 104729u * bid.z));
+    for (int i = n - 1; i > 0; i--) {
+      x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+      std::swap(w->perm[(size_t)i], w->perm[(size_t)(x % (uint64_t)(i + 1))]);
+    }
+  }
+  for (int slot = 0; slot < n; slot++) {
+    Fiber &f = w->fibers[(size_t)slot];
+    const int i = w->perm[(size_t)slot];
     f.done = false;
     f.tls.lin = i;
     f.tls.lane = i & 31;
@@ -202,8 +245,13 @@ void run_cta(Worker *w, dim3 block, dim3 bid, const std::function<void()> *body)
     f.tls.bid = bid;
     f.ctx.prepare(f.stack, FIBER_STACK, fiber_main);
   }
+  w->pending.clear();
   tlsp = &w->fibers[0].tls;
   switch_context(w->main_ctx, w->fibers[0].ctx);  // returns when the last thread of the CTA has exited
+  if (!w->pending.empty()) {
+    fprintf(stderr, "cuda_emu: CTA (%u,%u,%u) exited with %zu bulk tensor copies nobody waited for\n", bid.x, bid.y, bid.z, w->pending.size());
+    abort();
+  }
   tlsp = nullptr;
 }
 
@@ -383,7 +431,10 @@ void mbar_init(uint64_t *bar, int count) {
   *bar = 0;
 }
 void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { mb_update(bar, (int64_t)bytes, true); }
+void tma_flush(uint64_t *bar);
 void mbar_wait(uint64_t *bar, uint32_t parity) {
+  // SPK_EMU_TMA=lazy: the copies that signal this barrier land now, at the latest moment the kernel allows
+  if (tma_lazy()) tma_flush(bar);
   // try_wait.parity(p) succeeds once the phase of parity p has completed: the current phase has the other parity
   while ((((uint32_t)*(volatile uint64_t *)bar) & 1u) == (parity & 1u)) yield_fiber("mbarrier wait");
 }
@@ -438,6 +489,40 @@ CUresult encode_tiled(CUtensorMap *map, CUtensorMapDataType dtype, cuuint32_t ra
 }
 }  // namespace
 
+namespace {
+void tma_copy(const TmapDesc &d, unsigned char *out, const int *coord, uint64_t total) {
+  uint32_t idx[5] = {0, 0, 0, 0, 0};
+  for (uint64_t e = 0; e < total / d.elem; e++) {
+    bool inside = true;
+    uint64_t off = 0;
+    for (int i = 0; i < (int)d.rank; i++) {
+      const long long c = (long long)coord[i] + idx[i];
+      if (c < 0 || c >= (long long)d.dims[i]) inside = false;
+      else off += (uint64_t)c * d.strides[i];
+    }
+    if (inside) memcpy(out + e * d.elem, d.base + off, d.elem);
+    else memset(out + e * d.elem, 0, d.elem);  // out-of-bound elements are filled with zeros
+    for (int i = 0; i < (int)d.rank; i++) {
+      if (++idx[i] < d.box[i]) break;
+      idx[i] = 0;
+    }
+  }
+}
+}  // namespace
+
+void tma_flush(uint64_t *bar) {
+  Worker *w = W;
+  for (size_t i = 0; i < w->pending.size();) {
+    if (w->pending[i].bar != bar) { i++; continue; }
+    const PendingCopy pc = w->pending[i];
+    w->pending.erase(w->pending.begin() + (long)i);
+    TmapDesc d;
+    memcpy(&d, pc.desc, sizeof d);
+    tma_copy(d, pc.dst, pc.coord, pc.bytes);
+    mb_update(pc.bar, -(int64_t)pc.bytes, false);  // complete_tx
+  }
+}
+
 void tma_load(void *dst, const void *tensor_map, uint64_t *bar, const int *coord, int rank) {
   TmapDesc d;
   memcpy(&d, tensor_map, sizeof d);
@@ -452,22 +537,21 @@ void tma_load(void *dst, const void *tensor_map, uint64_t *bar, const int *coord
     fprintf(stderr, "cuda_emu: bulk tensor copy destination misaligned or outside shared memory\n");
     abort();
   }
-  uint32_t idx[5] = {0, 0, 0, 0, 0};
-  for (uint64_t e = 0; e < total / d.elem; e++) {
-    bool inside = true;
-    uint64_t off = 0;
-    for (int i = 0; i < rank; i++) {
-      const long long c = (long long)coord[i] + idx[i];
-      if (c < 0 || c >= (long long)d.dims[i]) inside = false;
-      else off += (uint64_t)c * d.strides[i];
-    }
-    if (inside) memcpy(out + e * d.elem, d.base + off, d.elem);
-    else memset(out + e * d.elem, 0, d.elem);  // out-of-bound elements are filled with zeros
-    for (int i = 0; i < rank; i++) {
-      if (++idx[i] < d.box[i]) break;
-      idx[i] = 0;
-    }
+  if (tma_lazy()) {
+    // the copy is in flight: its destination holds neither the old nor the new contents for anybody who does not wait
+    memset(out, 0xCB, total);
+    PendingCopy pc;
+    pc.dst = out;
+    memset(pc.desc, 0, sizeof pc.desc);
+    memcpy(pc.desc, &d, sizeof d);
+    for (int i = 0; i < 5; i++) pc.coord[i] = i < rank ? coord[i] : 0;
+    pc.rank = rank;
+    pc.bar = bar;
+    pc.bytes = total;
+    W->pending.push_back(pc);
+    return;
   }
+  tma_copy(d, out, coord, total);
   mb_update(bar, -(int64_t)total, false);  // complete_tx
 }
 
@@ -801,6 +885,42 @@ int spk_emu_selftest(void) {
   if (__funnelshift_l(0x80000000u, 0x00000001u, 1) != 0x00000003u || __funnelshift_r(0x00000003u, 0x00000001u, 1) != 0x80000001u)
     return 11;
   return 0;
+}
+// which CUDA thread of a 64-thread CTA runs first (SPK_EMU_ORDER), and whether a bulk tensor copy is visible before
+// its barrier has been waited for (SPK_EMU_TMA=lazy: no): first * 2 + visible
+int spk_emu_probe_modes(void) {
+  int first = -1, visible = -1;
+  int32_t *buf = nullptr;
+  cudaMalloc(&buf, 64 * 4);
+  for (int i = 0; i < 64; i++) buf[i] = 1000 + i;
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, nullptr);
+  CUtensorMap m;
+  cuuint64_t dims[1] = {64};
+  cuuint32_t box[1] = {64}, estr[1] = {1};
+  ((encode_fn)fn)(&m, CU_TENSOR_MAP_DATA_TYPE_INT32, 1, buf, dims, nullptr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  emu::launch("probe", nullptr, dim3(1), dim3(64), 64 * 4 + 64, [&]() {
+    if (first < 0) first = (int)threadIdx.x;
+    unsigned char *smem = emu::dynamic_smem();
+    int32_t *tile = reinterpret_cast<int32_t *>(smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 64 * 4);
+    if (threadIdx.x == 0) {
+      emu::mbar_init(bar, 1);
+      emu::mbar_expect_tx(bar, 64 * 4);
+      const int c[1] = {0};
+      emu::tma_load(tile, &m, bar, c, 1);
+      visible = tile[5] == 1005;
+    }
+    __syncthreads();
+    emu::mbar_wait(bar, 0);
+    if (tile[threadIdx.x] != 1000 + (int)threadIdx.x) visible = -100;
+  });
+  cudaFree(buf);
+  return first * 2 + visible;
 }
 // reads one byte at `offset` of a fresh 100-byte allocation (the test of SPK_EMU_GUARD: outside -> fault)
 int spk_emu_guard_probe(long offset) {

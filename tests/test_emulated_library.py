@@ -82,6 +82,29 @@ def test_guard_pages_fault_on_accesses_outside_an_allocation(emu_lib, guard, ins
     assert bad.returncode == -11, (bad.returncode, bad.stdout, bad.stderr)
 
 
+@pytest.mark.parametrize("env,want", [({}, 0 * 2 + 1), ({"SPK_EMU_ORDER": "reverse"}, 63 * 2 + 1), ({"SPK_EMU_TMA": "lazy"}, 0 * 2 + 0)])
+def test_order_and_lazy_copy_modes_do_what_they_say(emu_lib, env, want):
+    """SPK_EMU_ORDER decides which CUDA thread of a CTA runs first; with SPK_EMU_TMA=lazy a bulk tensor copy is not
+    visible until its barrier has been waited for (and the destination is poisoned meanwhile)"""
+    code = "import ctypes as C; print(C.CDLL(%r).spk_emu_probe_modes())" % emu_lib
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and int(r.stdout.strip()) == want, r.stdout + r.stderr
+
+
+def test_gpu_parity_tests_under_shuffled_threads_and_lazy_copies(emu_lib):
+    """a slice of the parity tests with the threads of every CTA started in a shuffled order and the bulk tensor
+    copies landing only when their barrier is waited for: a kernel that misses a barrier, reads a tile before its
+    copy has been waited for, or lets a copy overwrite planes still in use computes something else here"""
+    saved = dict(os.environ)
+    os.environ.update(SPK_EMU_ORDER="shuffle:7", SPK_EMU_TMA="lazy")
+    try:
+        n = _run_gpu_tests(emu_lib, ["tests/test_gpu_parity.py", "-k", "interleaved or large_lattices or extreme or elimination or per_colour"])
+    finally:
+        os.environ.clear()
+        os.environ.update(saved)
+    assert n >= 20
+
+
 def test_gpu_parity_tests_with_guard_pages(emu_lib):
     """a slice of the parity tests (shadows interleaved with int32 calls, masks, several-tile lattices, ...) with an inaccessible page behind
     every device allocation: no kernel reads or writes past the end of the lattice, its ghost layers, the shadows"""
