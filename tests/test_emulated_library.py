@@ -91,30 +91,19 @@ def test_order_and_lazy_copy_modes_do_what_they_say(emu_lib, env, want):
     assert r.returncode == 0 and int(r.stdout.strip()) == want, r.stdout + r.stderr
 
 
-def test_gpu_parity_tests_under_shuffled_threads_and_lazy_copies(emu_lib):
-    """a slice of the parity tests with the threads of every CTA started in a shuffled order and the bulk tensor
-    copies landing only when their barrier is waited for: a kernel that misses a barrier, reads a tile before its
-    copy has been waited for, or lets a copy overwrite planes still in use computes something else here"""
+def test_gpu_parity_tests_under_shuffled_threads_lazy_copies_and_guard_pages(emu_lib):
+    """a slice of the parity tests (shadows interleaved with int32 calls, masks, several-tile lattices, ...) with
+    the emulator's three checks on at once: the threads of every CTA started in a shuffled order, bulk tensor
+    copies landing only when their barrier is waited for (a kernel that misses a barrier, reads a tile early or
+    lets a copy overwrite planes still in use computes something else), and an inaccessible page behind every
+    device allocation (no kernel reads or writes past the end of the lattice, its ghost layers, the shadows)"""
     saved = dict(os.environ)
-    os.environ.update(SPK_EMU_ORDER="shuffle:7", SPK_EMU_TMA="lazy")
-    try:
-        n = _run_gpu_tests(emu_lib, ["tests/test_gpu_parity.py", "-k", "interleaved or large_lattices or extreme or elimination or per_colour"])
-    finally:
-        os.environ.clear()
-        os.environ.update(saved)
-    assert n >= 20
-
-
-def test_gpu_parity_tests_with_guard_pages(emu_lib):
-    """a slice of the parity tests (shadows interleaved with int32 calls, masks, several-tile lattices, ...) with an inaccessible page behind
-    every device allocation: no kernel reads or writes past the end of the lattice, its ghost layers, the shadows"""
-    env_guard = dict(os.environ)
-    os.environ["SPK_EMU_GUARD"] = "after"
+    os.environ.update(SPK_EMU_ORDER="shuffle:7", SPK_EMU_TMA="lazy", SPK_EMU_GUARD="after")
     try:
         n = _run_gpu_tests(emu_lib, ["tests/test_gpu_parity.py", "-k", "interleaved or masked or large_lattices or extreme or elimination or nloop or edge_sizes or per_colour"])
     finally:
         os.environ.clear()
-        os.environ.update(env_guard)
+        os.environ.update(saved)
     assert n >= 30
 
 
