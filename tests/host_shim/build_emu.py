@@ -26,9 +26,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-CSRC = os.path.join(ROOT, "spparks_b200", "csrc")
+# (the two overrides are for mutation experiments: build a patched copy of the sources somewhere else)
+CSRC = os.environ.get("SPK_EMU_CSRC") or os.path.join(ROOT, "spparks_b200", "csrc")
 EMU = os.path.join(HERE, "emu")
-BUILD = os.path.join(HERE, "_build")
+BUILD = os.environ.get("SPK_EMU_BUILD_DIR") or os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libspparks_cuda_emu.so")
 NCCL_LIB = os.path.join(BUILD, "libnccl_emu.so")  # for SPK_CUDA_NCCL_LIB: ranks = processes of this host
 UNITS = ["spk_cuda.cu", "model_ising.cu", "model_potts.cu", "model_potts_neighonly.cu", "model_potts_pin.cu",

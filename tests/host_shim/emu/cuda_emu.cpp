@@ -371,6 +371,16 @@ void launch(const char *label, const void *fn, dim3 grid, dim3 block, size_t sme
     return;
   }
   const std::string kernel = kernel_name(label, fn);
+  // SPK_EMU_JITTER=usec: a random pause before every launch (scale usec), different in every process: ranks that are
+  // processes drift apart, so an ordering between ranks that only held by accident breaks
+  static const long jitter_us = [] { const char *e = getenv("SPK_EMU_JITTER"); return e ? atol(e) : 0L; }();
+  if (jitter_us > 0) {
+    static uint64_t x = 0x9E3779B97F4A7C15ull * (uint64_t)(getpid() + 1);
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    // mostly short, one launch in sixteen long: a rank that stalls now and then, as a busy GPU does
+    const uint64_t span = (x >> 40) % 16 == 0 ? 8 * (uint64_t)jitter_us : (uint64_t)jitter_us / 8 + 1;
+    std::this_thread::sleep_for(std::chrono::microseconds((long)(x % span)));
+  }
   std::unique_lock<std::mutex> lk(pool.mu);
   launch_log[kernel]++;
   if (trace) fprintf(stderr, "cuda_emu: %s grid (%u,%u,%u) block (%u,%u,%u) smem %zu\n", kernel.c_str(), grid.x, grid.y, grid.z, block.x,
