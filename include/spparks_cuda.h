@@ -74,6 +74,10 @@ int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n);
 int spk_cuda_download_spins(spk_cuda_handle *h, int32_t *host, int64_t n);
 /* `temperature` (src/app_lattice.cpp:889-894): rebuilds the exp() acceptance tables on the host */
 int spk_cuda_set_temperature(spk_cuda_handle *h, double temperature);
+/* the integer acceptance thresholds the Philox-mode kernels compare the second word with:
+ * thr[dE] = floor(exp(-dE/T) * 2^32) for dE = 0 .. n-1 (n <= 27), from the host's libm
+ * (exp((einitial-efinal)*t_inverse), src/app_potts.cpp:130); all 0 beyond dE = 0 at T = 0.  For tests. */
+int spk_cuda_accept_thresholds(const spk_cuda_handle *h, uint32_t *thr, int n);
 
 /* `set site range lo hi` ON THE DEVICE, bit for bit the reference's values (src/set.cpp:582-627,
  * default loop all / no region, fraction or condition): the one Park-Miller stream that Set walks

@@ -12,6 +12,18 @@
 
 namespace spk {
 
+// Test switches (read at every launch so that tests can change them): small lattices otherwise take
+// neither the multi-step items (several class planes streamed through the ring by one item) nor the
+// loop over several items per CTA — the paths every BASELINE-size run lives on.
+//   SPK_CUDA_MAX_PLANE_CHUNKS=n  at most n chunks of class planes per tile (1: one item streams all planes)
+//   SPK_CUDA_MAX_CTAS=n          at most n CTAs per persistent launch
+inline int env_cap(const char *name, int value) {
+  const char *e = getenv(name);
+  const int v = e ? atoi(e) : 0;
+  return v > 0 && v < value ? v : value;
+}
+
+
 // sites of colour c0 inside the local box (nattempt += nselect, src/app_lattice.cpp:677)
 template <int LAT> int64_t class_count(const spk_cuda_handle *h, const Box &b, int c0) {
   auto par = [](int lo, int hi, int p) -> int64_t {  // # of x in [lo,hi) with x%2 == p
@@ -86,7 +98,7 @@ int launch_tile2d(spk_cuda_handle *h, const SweepArgs &a, int part) {
         return 1;
       h->smem_attr_set[0] = true;
     }
-    const int grid_max = 3 * 148;
+    const int grid_max = env_cap("SPK_CUDA_MAX_CTAS", 3 * 148);
     const int grid = tm.items < grid_max ? tm.items : grid_max;
     int32_t *dst = h->base_alt + (int64_t)h->gh * h->plane;
     sweep_tile2d_kernel<LAT, MODEL><<<grid, 256, C::SMEM_BYTES, h->stream>>>(h->tmap, a, tm, dst);
@@ -139,11 +151,13 @@ int launch_stream(spk_cuda_handle *h, const SweepArgs &a, bool pair = false) {
       sm.nty = (g.Y + C::YT - 1) / C::YT;
       int nzc = (items_per_cta * grid_max + sm.ntx * sm.nty - 1) / (sm.ntx * sm.nty);
       if (nzc > nq) nzc = nq;
+      nzc = env_cap("SPK_CUDA_MAX_PLANE_CHUNKS", nzc);
       if (nzc < 1) nzc = 1;
       sm.qchunk = (nq + nzc - 1) / nzc;
       sm.nzc = (nq + sm.qchunk - 1) / sm.qchunk;
       sm.items = sm.ntx * sm.nty * sm.nzc;
-      const int grid = sm.items < grid_max ? sm.items : grid_max;
+      const int grid_cap = env_cap("SPK_CUDA_MAX_CTAS", grid_max);
+      const int grid = sm.items < grid_cap ? sm.items : grid_cap;
       if constexpr (pr) {  // tile-edge words first (stream order: they see the lattice before the pair launch)
         sm.nrows = g.Y / 2;
         const size_t words = 2 * (size_t)sm.ntx * sm.nrows * sm.nq;
@@ -251,11 +265,13 @@ template <int MODEL> int launch_stream16(spk_cuda_handle *h, int color, const in
     const int grid_max = 2 * 148;
     int nzc = (items_per_cta * grid_max + sm.ntx * sm.nty - 1) / (sm.ntx * sm.nty);
     if (nzc > nq) nzc = nq;
+    nzc = env_cap("SPK_CUDA_MAX_PLANE_CHUNKS", nzc);
     if (nzc < 1) nzc = 1;
     sm.qchunk = (nq + nzc - 1) / nzc;
     sm.nzc = (nq + sm.qchunk - 1) / sm.qchunk;
     sm.items = sm.ntx * sm.nty * sm.nzc;
-    const int grid = sm.items < grid_max ? sm.items : grid_max;
+    const int grid_cap = env_cap("SPK_CUDA_MAX_CTAS", grid_max);
+    const int grid = sm.items < grid_cap ? sm.items : grid_cap;
     Sweep16Args a;
     a.spin = h->shadow; a.g = g; a.c0 = c0; a.ev = h->ev; a.naccept = h->naccept;
     a.mirror_lo = h->mirror_active ? h->mirror16_lo : nullptr;

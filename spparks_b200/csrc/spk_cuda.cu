@@ -643,6 +643,13 @@ int spk_cuda_download_spins(spk_cuda_handle *h, int32_t *host, int64_t n) {
   return 0;
 }
 
+int spk_cuda_accept_thresholds(const spk_cuda_handle *h, uint32_t *thr, int n) {
+  if (!h || !thr) return fail("null argument");
+  if (n < 1 || n > 27) return fail("thresholds exist for dE = 0 .. 26");
+  for (int dE = 0; dE < n; dE++) thr[dE] = h->ev.thr[dE];
+  return 0;
+}
+
 int spk_cuda_set_temperature(spk_cuda_handle *h, double temperature) {
   if (!h) return fail("null handle");
   if (temperature < 0.0) return fail("temperature must be >= 0");

@@ -128,6 +128,12 @@ def test_cluster_tests_pass_on_the_emulated_library(emu_lib):
     assert _run_gpu_tests(emu_lib, ["tests/test_cluster.py", "-k", "not large"]) >= 12
 
 
+def test_more_parity_tests_pass_on_the_emulated_library(emu_lib):
+    """tests/test_zz_more_parity.py: multi-step work items, several items per CTA, y extents of whole tiles,
+    every face of every sector's mask border, the acceptance threshold table"""
+    assert _run_gpu_tests(emu_lib, ["tests/test_zz_more_parity.py"]) >= 84
+
+
 def test_device_pin_tests_pass_on_the_emulated_library(emu_lib):
     """device-side `pin f multi nthresh` against the reference's pinned sites (fixtures), the oracle, and through
     the plugin's `cuda_pin` against the reference binary's `pin`"""
