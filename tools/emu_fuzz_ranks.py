@@ -46,9 +46,14 @@ def draw_case(rng, world):
         ny = 2 * world * int(rng.integers(2, 9))            # even slabs of 4 .. 16 rows (>= the 4 ghost rows)
         nz = 1
     q = 2 if model.startswith("ising") else int(rng.choice([2, 3, 5, 50, 10000, 65533, 65534, 70000]))
+    tier = "tuned" if rng.random() < 0.5 else list(TIERS)[int(rng.integers(len(TIERS)))]
+    halo = str(rng.choice(["p2p", "p2p", "nccl"]))
+    if rng.random() < 0.15:  # the 16-bit shadow on several ranks (neighbours store into each other's shadow ghost planes)
+        lat, model, tier, halo = "sc/26n", str(rng.choice(["potts", "potts/pin"])), "tuned", "p2p"
+        nx, ny, nz = int(rng.choice([8, 16, 24, 264])), int(rng.choice([2, 6, 16, 32, 34])), 2 * world * int(rng.integers(1, 5))
+        q = int(rng.choice([3, 50, 10000, 65533]))
     return {"lat": lat, "model": model, "n": [nx, ny, nz], "q": q, "T": float(rng.choice([0.0, 0.4, 1.0, 5.0])),
-            "tier": "tuned" if rng.random() < 0.5 else list(TIERS)[int(rng.integers(len(TIERS)))],
-            "halo": str(rng.choice(["p2p", "p2p", "nccl"])), "seed": int(rng.integers(1, 2**40)),
+            "tier": tier, "halo": halo, "seed": int(rng.integers(1, 2**40)),
             "calls": [int(x) for x in rng.integers(1, 4, size=int(rng.integers(1, 4)))],   # sweeps per spk_cuda_sweeps call
             "between": [str(x) for x in rng.choice(["none", "energy", "clusters", "download"], size=3)],
             "start": str(rng.choice(["random", "few", "grains"])),
@@ -175,7 +180,7 @@ def main():
     spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "host_shim", "build_emu.py"))
     be = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(be)
-    lib = be.build()
+    lib = os.environ.get("SPK_EMU_USE_LIB") or be.build()  # (the override: tools/emu_mutants.py)
     rng = np.random.default_rng(args.seed)
     cases = [draw_case(rng, args.ranks) for _ in range(args.cases)]
     arena = tempfile.mkdtemp(prefix="spk_emu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)

@@ -7,6 +7,7 @@ Each mutant is the library's source with ONE small defect planted in a kernel or
 built for the host (tests/host_shim/build_emu.py with SPK_EMU_CSRC / SPK_EMU_BUILD_DIR, the tree is
 not touched) and tests/test_zz_more_parity.py + tests/test_gpu_parity.py run against it (a survivor once more
 under shuffled threads and lazy copies): a mutant is KILLED when a test fails.
+A survivor of the one-rank files also meets 60 random two-rank cases (tools/emu_fuzz_ranks.py).
 A survivor is a hole in the tests (or an equivalent mutant) and is printed as such.  This says how
 much a green run of the emulated tier is worth; it is test infrastructure, not product.
 """
@@ -44,10 +45,10 @@ MUTANTS = [
     ("sweep_tiled.cuh", "const int eL = e0 == 0 ? rowlen - 4 : e0 - 4;", "const int eL = e0 == 0 ? rowlen - 8 : e0 - 4;", "strip kernel: left periodic halo chunk taken one chunk early"),
     ("sweep_tiled.cuh", "const int eR = e0 + 8 == rowlen ? 0 : e0 + 8;", "const int eR = e0 + 8 == rowlen ? 4 : e0 + 8;", "strip kernel: right periodic halo chunk off by one chunk"),
     ("sweep_tile2d.cuh", "      __syncthreads();\n    }\n\n    // store the interior", "    }\n\n    // store the interior", "colour-fused 2-D kernel: barrier between colour steps dropped"),
-    ("sweep_tile2d.cuh", "const int ylo = c0 + 1, yhi = C::BH - c0 - 1;", "const int ylo = c0 + 1, yhi = C::BH - c0;", "colour-fused 2-D kernel: a colour step updates one stale halo row too many"),
+    ("sweep_tile2d.cuh", "const int ylo = c0 + 1, yhi = C::BH - c0 - 1;", "const int ylo = c0 + 1, yhi = C::BH - c0;", "[equivalent] colour-fused 2-D kernel: a colour step updates one halo row too many (the row is never stored and only later halo rows read it)"),
     ("sweep_tile2d.cuh", "if (++jg == g.gY) jg = 0;", "if (++jg == g.gY + 1) jg = 0;", "colour-fused 2-D kernel: global row of the random stream does not wrap"),
     ("sweep_tile2d.cuh", "    __syncthreads();  // the tile buffer is reused by the next item", "    // (barrier dropped)", "colour-fused 2-D kernel: barrier before the tile buffer is reused dropped"),
-    ("sweep_generic.cuh", "int px = (c0 + j + k + g.g0) & 1;           // (i + j + kglobal) % 2 == c0", "int px = (c0 + j + k) & 1;           // (i + j + kglobal) % 2 == c0", "generic kernel: sc/6n colour parity ignores the slab offset (only visible on several ranks; expected to SURVIVE one-rank tests)"),
+    ("sweep_generic.cuh", "int px = (c0 + j + k + g.g0) & 1;           // (i + j + kglobal) % 2 == c0", "int px = (c0 + j + k) & 1;           // (i + j + kglobal) % 2 == c0", "[equivalent] generic kernel: sc/6n colour parity ignores the slab offset (slabs are even, so is every offset)"),
     ("sweep_generic.cuh", "const unsigned long long leader = gsite - (unsigned long long)(philox_leader_shift<MODEL>(i) * NB);", "const unsigned long long leader = gsite - (unsigned long long)(philox_leader_shift<MODEL>(i));", "generic kernel: Philox block leader ignores the basis (tri)"),
     ("sweep_stream16.cuh", "dst[i] = make_uint4((uint32_t)a.x | ((uint32_t)a.y << 16), (uint32_t)a.z | ((uint32_t)a.w << 16),", "dst[i] = make_uint4((uint32_t)a.y | ((uint32_t)a.x << 16), (uint32_t)a.z | ((uint32_t)a.w << 16),", "shadow pack: first two sites of a chunk swapped"),
     ("sweep_bits2d.cuh", "const uint32_t even = p0 ? w1 : w0, odd = p0 ? w0 : w1;", "const uint32_t even = p0 ? w0 : w1, odd = p0 ? w1 : w0;", "bit-shadow unpack: colours swapped in odd rows"),
@@ -55,8 +56,8 @@ MUTANTS = [
     ("aux_kernels.cuh", "uint32_t state = pm_mulmod(seed0, pm_powmod(16807u, first_draw + (unsigned long long)(first + lane) + 1ull));", "uint32_t state = pm_mulmod(seed0, pm_powmod(16807u, first_draw + (unsigned long long)(first + lane)));", "device pin: draw numbers shifted by one"),
     ("aux_kernels.cuh", "e += (spin[zk[o.dz + 1] * sz + yj[o.dy + 1] * sy + (long long)xi[o.dx + 1] * NB + o.m] != me);\n      }\n    }\n  }\n  e = __reduce_add_sync", "e += (spin[zk[o.dz + 1] * sz + yj[o.dy + 1] * sy + (long long)xi[o.dx + 1] * NB] != me);\n      }\n    }\n  }\n  e = __reduce_add_sync", "energy kernel: neighbour basis ignored (tri)"),
     ("cluster.cuh", "const unsigned peers = __match_any_sync(0xffffffffu, r);", "const unsigned peers = __match_any_sync(0xffffffffu, r) | 1u;", "clusters: warp-aggregated volume counts lane 0 everywhere"),
-    ("spk_cuda.cu", "if (h->kstat_mean < h->neigh_switch - 0.25) h->neigh_adaptive = true;", "if (h->kstat_mean < h->neigh_switch - 0.25) h->neigh_adaptive = false;", "host: automatic variant switch never switches (same spins either way: expected to SURVIVE parity tests)"),
-    ("spk_cuda.cu", "  h->canon_current = false;\n    // the conversion above rewrites", "  // (stale flag dropped)\n    // the conversion above rewrites", "host: int32 lattice not marked stale after multi-rank shadow sweeps (several ranks only: expected to SURVIVE)"),
+    ("spk_cuda.cu", "if (h->kstat_mean < h->neigh_switch - 0.25) h->neigh_adaptive = true;", "if (h->kstat_mean < h->neigh_switch - 0.25) h->neigh_adaptive = false;", "[equivalent] host: automatic variant switch never switches (both variants give the same spins; speed only)"),
+    ("spk_cuda.cu", "  h->canon_current = false;\n    // the conversion above rewrites", "  // (stale flag dropped)\n    // the conversion above rewrites", "host: int32 lattice not marked stale after shadow sweeps on several ranks (only the multi-rank cases can see it)"),
     ("spk_cuda.cu", "ev.thr[dE] = t > 4294967295.0 ? 4294967295u : (uint32_t)t;", "ev.thr[dE] = t > 4294967295.0 ? 4294967295u : (uint32_t)t + 1u;", "host: acceptance thresholds one too high"),
 ]
 
@@ -103,12 +104,17 @@ def main():
                     dead, how = True, "timeout (hang)"
                 if dead:
                     break
+            if not dead:  # last chance: several ranks (random cases of tools/emu_fuzz_ranks.py, both halo modes)
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emu_fuzz_ranks.py"), "--ranks", "2", "--cases", "60", "--seed", "5"],
+                                   cwd=ROOT, env=dict(os.environ, SPK_EMU_USE_LIB=env["SPK_CUDA_LIB"]), capture_output=True, text=True)
+                dead = r.returncode != 0
+                how = "2 ranks: " + (r.stdout.strip().splitlines() or ["?"])[0]
             print("mutant %2d  %s: %s   [%s]" % (k, "KILLED" if dead else "SURVIVED", what, how[:100]), flush=True)
-            if not dead:
+            if not dead and not what.startswith("[equivalent]"):
                 survivors.append(k)
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
-    print("%d mutants, %d survived %s" % (last - first + 1, len(survivors), survivors))
+    print("%d mutants, %d unexpected survivors %s" % (last - first + 1, len(survivors), survivors))
     return 1 if survivors else 0
 
 
