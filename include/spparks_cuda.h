@@ -74,6 +74,13 @@ int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n);
 int spk_cuda_download_spins(spk_cuda_handle *h, int32_t *host, int64_t n);
 /* `temperature` (src/app_lattice.cpp:889-894): rebuilds the exp() acceptance tables on the host */
 int spk_cuda_set_temperature(spk_cuda_handle *h, double temperature);
+/* init_app's check of the site values (src/app_potts.cpp:83-90, src/app_ising.cpp:74-81,
+ * src/app_potts_pin.cpp:78-84) on the device lattice: error if a spin lies outside 1..Q (Q+1: pinned) */
+int spk_cuda_validate_spins(spk_cuda_handle *h);
+/* key of the counter-based random stream of the Philox-mode sweeps (spk_cuda_desc::seed), changed after
+ * creation: a lattice created before the point where a script's `seed`-derived draws are due (the
+ * plugin's cuda_create_sites) gets the seed the host path would have used */
+int spk_cuda_set_seed(spk_cuda_handle *h, uint64_t seed);
 /* the integer acceptance thresholds the Philox-mode kernels compare the second word with:
  * thr[dE] = floor(exp(-dE/T) * 2^32) for dE = 0 .. n-1 (n <= 27), from the host's libm
  * (exp((einitial-efinal)*t_inverse), src/app_potts.cpp:130); all 0 beyond dE = 0 at T = 0.  For tests. */

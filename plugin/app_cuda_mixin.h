@@ -23,6 +23,7 @@
 
 #include "mpi.h"
 #include "string.h"
+#include "math.h"
 #include "stdlib.h"
 #include "stdint.h"
 #include "app_lattice.h"
@@ -30,6 +31,7 @@
 #include "domain.h"
 #include "lattice.h"
 #include "random_mars.h"
+#include "random_park.h"
 // output.h has no include guard in the reference: input.cpp includes it before style_app.h
 #include "timer.h"
 #include "error.h"
@@ -70,6 +72,8 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     sweep_counter = 0;
     warned = 0;
     device_current = 0;
+    device_only = 0;
+    dev_nloop = 1;
   }
 
   virtual ~AppCudaMixin()
@@ -92,10 +96,18 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       // no region/fraction/if), computed on the device: same master-stream draw, same values
       if (narg != 4 || strcmp(arg[0],"site") != 0 || strcmp(arg[1],"range") != 0)
         this->error->all(FLERR,"Illegal cuda_set command (cuda_set site range lo hi)");
-      if (this->sites_exist == 0) this->error->all(FLERR,"Set command before sites exist");
+      if (this->sites_exist == 0 && !device_only) this->error->all(FLERR,"Set command before sites exist");
       int lo = atoi(arg[2]), hi = atoi(arg[3]);
       int pseed = static_cast<int> (this->ranmaster->uniform()*2147483647);   // new RandomPark(double)
       if (pseed == 0) pseed = 1;
+      if (device_only) {      // the lattice lives on the device: nothing to bring back
+        check(spk_cuda_set_site_range(handle,pseed,lo,hi));
+        if (this->me == 0) {
+          if (this->screen) fprintf(this->screen,"  " TAGINT_FORMAT " settings made for site\n",this->nglobal);
+          if (this->logfile) fprintf(this->logfile,"  " TAGINT_FORMAT " settings made for site\n",this->nglobal);
+        }
+        return;
+      }
       spk_cuda_handle *tmp = NULL;
       spk_cuda_desc desc;
       fill_desc(desc,0.0);
@@ -116,13 +128,18 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       // generator, same pinned sites.  multi = 1 and nthresh > 0 depend on the order of the attempts:
       // one rank only (the library says so)
       if (narg != 3) this->error->all(FLERR,"Illegal pin command");
-      if (this->sites_exist == 0) this->error->all(FLERR,"Pin command before sites exist");
+      if (this->sites_exist == 0 && !device_only) this->error->all(FLERR,"Pin command before sites exist");
       double pfrac = atof(arg[0]);
       int pmulti = atoi(arg[1]), pthresh = atoi(arg[2]);
       if (pfrac < 0.0 || pfrac > 1.0 || (pmulti != 0 && pmulti != 1) || pthresh < 0)
         this->error->all(FLERR,"Illegal pin command");
       int pseed = static_cast<int> (this->ranmaster->uniform()*2147483647);   // new RandomPark(double), :248
       if (pseed == 0) pseed = 1;
+      if (device_only) {
+        int64_t np = 0;
+        check(spk_cuda_pin_create(handle,pfrac,pmulti,pthresh,pseed,&np));
+        return;
+      }
       spk_cuda_handle *tmp = NULL;
       spk_cuda_desc desc;
       fill_desc(desc,0.0);
@@ -140,6 +157,54 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       if (!rc) rc = spk_cuda_download_spins(tmp,this->iarray[0],this->nlocal);
       spk_cuda_destroy(tmp);
       check(rc);
+    } else if (strcmp(command,"cuda_create_sites") == 0) {
+      // cuda_create_sites  ==  create_sites box  for a lattice that lives on the device ONLY:
+      // no per-site host arrays (id, xyz, neighbor lists: 148 bytes per site and 32-bit indices in
+      // the reference, src/create_sites.cpp:198-498), so that the BASELINE lattices (1024^3 and up)
+      // can be driven from an input script.  Geometry as CreateSites::structured_lattice
+      // (:229-252): fully periodic box, a whole number of lattice cells.  What needs the host
+      // copy afterwards is refused by the reference itself ("... before sites exist": set, dump,
+      // the host diagnostics); cuda_set, cuda_pin, diag_style energy/cuda and cluster/cuda work.
+      if (narg != 0) this->error->all(FLERR,"Illegal cuda_create_sites command");
+      Domain *domain = this->domain;
+      if (domain->box_exist == 0) this->error->all(FLERR,"Create_sites command before simulation box is defined");
+      if (this->sites_exist || device_only) this->error->all(FLERR,"Cannot create sites after sites already exist");
+      if (domain->lattice == NULL) this->error->all(FLERR,"Cannot create sites with undefined lattice");
+      if (domain->nonperiodic) this->error->all(FLERR,"cuda_create_sites needs a fully periodic box");
+      int dim = domain->dimension;
+      double xl = domain->lattice->xlattice, yl = domain->lattice->ylattice, zl = domain->lattice->zlattice;
+      int nx = static_cast<int> (domain->xprd / xl);
+      int ny = dim >= 2 ? static_cast<int> (domain->yprd / yl) : 1;
+      int nz = dim == 3 ? static_cast<int> (domain->zprd / zl) : 1;
+      if (fabs(nx*xl - domain->xprd) > 0.0001*xl || (dim > 1 && fabs(ny*yl - domain->yprd) > 0.0001*yl) ||
+          (dim > 2 && fabs(nz*zl - domain->zprd) > 0.0001*zl))
+        this->error->all(FLERR,"Periodic box is not a multiple of lattice spacing");
+      domain->nx = nx; domain->ny = ny; domain->nz = nz;
+      int lat = domain->lattice->style;
+      if (spk_cuda_maxneigh(lat) == 0) this->error->all(FLERR,"app_style */cuda does not support this lattice style");
+      this->maxneigh = spk_cuda_maxneigh(lat);
+      bigint nbig = (bigint) nx * ny * nz * spk_cuda_nbasis(lat);
+      if (nbig > MAXTAGINT) this->error->all(FLERR,"Too many sites for the site ID type (tagint)");
+      this->nglobal = (tagint) nbig;     // nlocal stays 0 and sites_exist 0: there are no host sites
+      spk_cuda_desc desc;
+      fill_desc(desc,this->temperature);
+      check(spk_cuda_create(&desc,&handle));
+      if (this->nprocs > 1) {
+        char id[SPK_CUDA_COMM_ID_BYTES];
+        if (this->me == 0) check(spk_cuda_comm_id(id));
+        MPI_Bcast(id,SPK_CUDA_COMM_ID_BYTES,MPI_CHAR,0,this->world);
+        check(spk_cuda_comm_init(handle,id));
+      }
+      // like iarray[0] after create_sites: every site 0 until `cuda_set` (the reference's init_app
+      // refuses such a lattice, and so does ours)
+      device_only = 1;
+      device_current = 1;
+      if (this->me == 0) {
+        if (this->screen) fprintf(this->screen,"Creating sites ...\n  " TAGINT_FORMAT " sites on the device (no host copy)\n  "
+                                  TAGINT_FORMAT " sites have %d neighbors\n",this->nglobal,this->nglobal,this->maxneigh);
+        if (this->logfile) fprintf(this->logfile,"Creating sites ...\n  " TAGINT_FORMAT " sites on the device (no host copy)\n  "
+                                   TAGINT_FORMAT " sites have %d neighbors\n",this->nglobal,this->nglobal,this->maxneigh);
+      }
     } else if (strcmp(command,"cuda_host_sync") == 0) {
       // yes (default): iarray[0] is refreshed before every Output::compute, as host-side
       //   diagnostics and dumps expect
@@ -163,9 +228,71 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     }
   }
 
+  // device lattice (cuda_create_sites): AppLattice::init / setup (src/app_lattice.cpp:133-442) without
+  // the per-site machinery (sets, comm lists, masks, site seeds) the host copy would need
+
+  void init()
+  {
+    if (!device_only) { Base::init(); return; }
+    enum{NOSWEEP,RANDOM,RASTER,COLOR,COLOR_STRICT};
+    if (this->solve) this->error->all(FLERR,"KMC events are not implemented in app");
+    if (this->sweepflag != COLOR)
+      this->error->all(FLERR,"app_style */cuda on a device lattice (cuda_create_sites) needs sweep color");
+    int dimension = this->domain->dimension;
+    this->nsector = 1;
+    if (this->sectorflag) {          // src/app_lattice.cpp:161-187
+      if (this->nsector_user) this->nsector = this->nsector_user;
+      else this->nsector = dimension == 2 ? 4 : 8;
+      if (dimension == 3 && ((this->nsector == 2 && (this->domain->procgrid[1] != 1 || this->domain->procgrid[2] != 1)) ||
+                             (this->nsector == 4 && this->domain->procgrid[2] != 1)))
+        this->error->all(FLERR,"Invalid number of sectors");
+      if (dimension == 2 && ((this->nsector == 2 && this->domain->procgrid[1] != 1) || this->nsector == 8))
+        this->error->all(FLERR,"Invalid number of sectors");
+    }
+    this->ncolors = this->domain->lattice->ncolors(this->delevent + this->delpropensity);
+    if (this->ncolors == 0) this->error->all(FLERR,"Cannot color this combination of lattice and app");
+    this->bothflag = (this->nsector > 1 && this->ncolors > 1) ? 1 : 0;
+    if (this->ranapp == NULL) {      // :274-278: the master generator ends up where the host path leaves it
+      this->ranapp = new RandomPark(this->ranmaster->uniform());
+      double rseed = this->ranmaster->uniform();
+      this->ranapp->reset(rseed,this->me,100);
+    }
+    init_app();
+    if (this->dt_sweep == 0.0) this->error->all(FLERR,"App did not set dt_sweep");
+    this->output->init(this->time);
+  }
+
+  void setup()
+  {
+    if (!device_only) { Base::setup(); return; }
+    this->setup_app();
+    int n = 1;                       // :401-410 for sweep color: nloop of every set
+    if (this->nstop > 0.0) n = static_cast<int> (this->nstop);
+    if (this->tstop > 0.0) n = static_cast<int> (this->tstop/this->dt_sweep);
+    dev_nloop = n;
+    this->dt_rkmc = (double) n * this->dt_sweep;      // every site is attempted n times per pass: ntotal/nglobal = n
+    if (this->dt_rkmc == 0.0) this->error->all(FLERR,"Choice of sector stop led to no rKMC events");
+    if (this->stoptime - this->time < this->dt_rkmc) this->dt_rkmc = this->stoptime - this->time;
+    this->setup_end_app();
+    this->nextoutput = this->output->setup(this->time,this->first_run);
+  }
+
   void init_app()
   {
     Base::init_app();   // spin validity check, dt_sweep of potts/neighonly
+
+    if (device_only) {
+      if (!seed_set) {
+        seed = (uint64_t) (this->ranmaster->uniform() * 9007199254740992.0);
+        seed_set = 1;
+      }
+      check(spk_cuda_set_seed(handle,seed));
+      check(spk_cuda_set_temperature(handle,this->temperature));
+      check(spk_cuda_mask_enable(handle,this->Lmask ? 1 : 0));
+      // init_app's spin check (src/app_potts.cpp:83-90), where the spins are
+      if (spk_cuda_validate_spins(handle) != 0) this->error->one(FLERR,"One or more sites have invalid values");
+      return;
+    }
 
     if (!seed_set) {
       // like ranapp (src/app_lattice.cpp:274-278): derived from the `seed` command, once
@@ -223,7 +350,7 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     }
 
     check(spk_cuda_set_temperature(handle,this->temperature));
-    check(spk_cuda_upload_spins(handle,this->iarray[0],this->nlocal));
+    if (!device_only) check(spk_cuda_upload_spins(handle,this->iarray[0],this->nlocal));
     device_current = 1;      // from here on the device is ahead or (after every download) equal
     if (strict) check(spk_cuda_set_siteseeds(handle,this->siteseeds,this->nlocal));
     check(spk_cuda_reset_counters(handle));
@@ -282,7 +409,7 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       if (done || this->time >= this->nextoutput) {
         // host copy must be current before host-side diagnostics and dumps read it
         // (cuda_host_sync no: only when the run ends)
-        if (host_sync || done)
+        if ((host_sync || done) && !device_only)
           check(spk_cuda_download_spins(handle,this->iarray[0],this->nlocal));
         int64_t acc,att;
         check(spk_cuda_counters(handle,&acc,&att));
@@ -318,7 +445,7 @@ class AppCudaMixin : public Base, public SpkCudaHost {
   spk_cuda_handle *cuda_lattice()
   {
     if (!handle) this->error->one(FLERR,"app_style */cuda: no device lattice before init");
-    if (!device_current) {
+    if (!device_current && !device_only) {
       check(spk_cuda_upload_spins(handle,this->iarray[0],this->nlocal));
       device_current = 1;
     }
@@ -328,6 +455,8 @@ class AppCudaMixin : public Base, public SpkCudaHost {
  private:
   spk_cuda_handle *handle;
   int device,nspins_cuda,seed_set,warned,device_current,host_sync;
+  int device_only;      // the lattice lives on the device only (cuda_create_sites): nlocal = 0 on the host
+  int dev_nloop;        // its nloop (setup)
   void *pinned;
   size_t pinned_bytes;
   double perf_sites,perf_seconds;
@@ -418,6 +547,7 @@ class AppCudaMixin : public Base, public SpkCudaHost {
   int set_nloop(int isector, int icolor, int ncolor)
   {
     enum{NOSWEEP,RANDOM,RASTER,COLOR,COLOR_STRICT};
+    if (device_only) return dev_nloop;
     int iset;
     if (this->sweepflag == COLOR || this->sweepflag == COLOR_STRICT) {
       if (this->bothflag) iset = this->nsector + isector*ncolor + icolor;

@@ -622,6 +622,14 @@ int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n) {
   neigh_mode_reset(h);
   // the reference's init_app refuses spins outside 1..Q (Q+1 = pinned for potts/pin); the kernels
   // rely on it (packed 16-bit compares), so the check is repeated where the spins enter the device
+  return spk_cuda_validate_spins(h);
+}
+
+int spk_cuda_validate_spins(spk_cuda_handle *h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->d.device));
+  if (use_canon(h, false)) return 1;
+  const long long n = h->nlocal;
   const int hi = ising_like(h->d.model) ? 2 : h->d.nspins + (h->d.model == SPK_POTTS_PIN ? 1 : 0);
   CU(cudaMemsetAsync(h->escratch, 0, sizeof(unsigned long long), h->stream));
   validate_kernel<<<148 * 8, 256, 0, h->stream>>>(h->spin, n, 1, hi, h->escratch);
@@ -629,7 +637,7 @@ int spk_cuda_upload_spins(spk_cuda_handle *h, const int32_t *host, int64_t n) {
   unsigned long long bad = 0;
   CU(cudaMemcpyAsync(&bad, h->escratch, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  if (bad) return fail("One or more sites have invalid values (%llu of %lld outside 1..%d)", bad, (long long)n, hi);
+  if (bad) return fail("One or more sites have invalid values (%llu of %lld outside 1..%d)", bad, n, hi);
   return 0;
 }
 
@@ -656,6 +664,15 @@ int spk_cuda_set_temperature(spk_cuda_handle *h, double temperature) {
   h->d.temperature = temperature;
   const uint32_t sweep = h->ev.sweep;
   build_tables(h);
+  h->ev.sweep = sweep;
+  return 0;
+}
+
+int spk_cuda_set_seed(spk_cuda_handle *h, uint64_t seed) {
+  if (!h) return fail("null handle");
+  h->d.seed = seed;
+  const uint32_t sweep = h->ev.sweep;
+  build_tables(h);  // the Philox key and its round keys
   h->ev.sweep = sweep;
   return 0;
 }
@@ -1200,8 +1217,6 @@ int spk_cuda_mask_enable(spk_cuda_handle *h, int on) {
   if (!on) {
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(h->mask_base);
-  cudaFree(h->shadow_base);
-  cudaFree(h->bits);
     h->mask_base = h->mask = nullptr;
     return 0;
   }

@@ -80,6 +80,9 @@ class LatticeSweep:
         _lib.check(self.L.spk_cuda_site_energy(self.h, out.ctypes.data_as(C.c_void_p), self.nlocal))
         return out
 
+    def set_seed(self, seed):
+        _lib.check(self.L.spk_cuda_set_seed(self.h, seed))
+
     def accept_thresholds(self, n=27):
         out = (C.c_uint32 * n)()
         _lib.check(self.L.spk_cuda_accept_thresholds(self.h, out, n))

@@ -128,10 +128,17 @@ def test_cluster_tests_pass_on_the_emulated_library(emu_lib):
     assert _run_gpu_tests(emu_lib, ["tests/test_cluster.py", "-k", "not large"]) >= 12
 
 
+@pytest.mark.skipif(not os.path.exists(SPK_CUDA), reason="plugin/_build/spk_cuda not built (needs the reference tree)")
+def test_device_lattice_scripts_pass_on_the_emulated_library(emu_lib):
+    """`cuda_create_sites`: scripts whose lattice lives on the device only print the table of the same script
+    with a host lattice (tests/test_zz_device_lattice.py)"""
+    assert _run_gpu_tests(emu_lib, ["tests/test_zz_device_lattice.py"]) >= 8
+
+
 def test_more_parity_tests_pass_on_the_emulated_library(emu_lib):
     """tests/test_zz_more_parity.py: multi-step work items, several items per CTA, y extents of whole tiles,
     every face of every sector's mask border, the acceptance threshold table"""
-    assert _run_gpu_tests(emu_lib, ["tests/test_zz_more_parity.py"]) >= 84
+    assert _run_gpu_tests(emu_lib, ["tests/test_zz_more_parity.py"]) >= 87
 
 
 def test_device_pin_tests_pass_on_the_emulated_library(emu_lib):

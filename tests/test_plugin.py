@@ -18,12 +18,14 @@ pytestmark = [pytest.mark.gpu,
                                  reason="plugin/_build/spk_cuda or oracle/_ref/spk_ref not built")]
 
 
-def run(binary, script):
+def run(binary, script, expect_error=False):
     with tempfile.TemporaryDirectory() as tmp:
         path = os.path.join(tmp, "in.script")
         open(path, "w").write(script)
         out = subprocess.run([binary, "-in", path, "-log", "none"], cwd=tmp, capture_output=True, text=True,
                              timeout=600)
+    if expect_error:
+        return out.stdout + out.stderr
     assert "ERROR" not in out.stdout, out.stdout[-2000:]
     return out.stdout
 

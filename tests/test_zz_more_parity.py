@@ -121,3 +121,39 @@ def test_acceptance_thresholds_are_the_oracles(T):
         for dE in range(1, 27):
             assert thr[dE] == O.accept_threshold(T, dE), dE
     s.close()
+
+
+@pytest.mark.parametrize("model,lat,n,q", [("potts", "sc/26n", (16, 8, 8), 20), ("potts/pin", "sc/26n", (8, 8, 8), 9),
+                                            ("ising", "sq/4n", (64, 16, 1), 2)], ids=lambda v: str(v).replace(" ", ""))
+def test_masks_switched_off_again(model, lat, n, q):
+    """spk_cuda_mask_enable(h, 0) after masked sweeps: the following sweeps run on the 16-bit / 1-bit shadow again
+    (switching the masks off once freed the shadows: found by the device-lattice mode of the plugin, which
+    switches them off at every init)"""
+    from spparks_b200 import LatticeSweep
+    o = O.Oracle(model, lat, n[0], n[1], n[2], q, 0.6)
+    rng = np.random.default_rng(3)
+    spins = np.repeat(rng.integers(1, (2 if model == "ising" else q) + 1, size=(o.nsites + 3) // 4, dtype=np.int32), 4)[:o.nsites].copy()
+    s = LatticeSweep(model, lat, n[0], n[1], n[2], nspins=q, temperature=0.6, seed=99)
+    s.upload(spins)
+    want = spins.copy()
+    s.sweeps(0, 1)
+    o.sweep_philox(want, 99, 0)
+    s.mask_enable(True)
+    mask = np.zeros(o.nsites, dtype=np.uint8)
+    ns = 8 if lat.startswith("sc") else 4
+    for isec in range(ns):
+        box = o.sector_box(ns, isec)
+        o.boundary_clear_mask(mask, box)
+        s.mask_clear_border(box, 0)
+        for color in range(1, o.ncolors + 1):
+            o.halfsweep_philox_mask(want, mask, 99, 1, color, 0, box)
+            s.sweep_color(1, color, box, 1)
+    assert np.array_equal(s.download(), want)
+    s.mask_enable(False)
+    for call in range(2):
+        s.sweeps(2 + 2 * call, 2)
+        for sw in range(2):
+            o.sweep_philox(want, 99, 2 + 2 * call + sw)
+        assert np.array_equal(s.download(), want), call
+    assert s.energy() == o.total_energy(want)
+    s.close()

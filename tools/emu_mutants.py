@@ -58,6 +58,7 @@ MUTANTS = [
     ("cluster.cuh", "const unsigned peers = __match_any_sync(0xffffffffu, r);", "const unsigned peers = __match_any_sync(0xffffffffu, r) | 1u;", "clusters: warp-aggregated volume counts lane 0 everywhere"),
     ("spk_cuda.cu", "if (h->kstat_mean < h->neigh_switch - 0.25) h->neigh_adaptive = true;", "if (h->kstat_mean < h->neigh_switch - 0.25) h->neigh_adaptive = false;", "[equivalent] host: automatic variant switch never switches (both variants give the same spins; speed only)"),
     ("spk_cuda.cu", "  h->canon_current = false;\n    // the conversion above rewrites", "  // (stale flag dropped)\n    // the conversion above rewrites", "host: int32 lattice not marked stale after shadow sweeps on several ranks (only the multi-rank cases can see it)"),
+    ("spk_cuda.cu", "    cudaFree(h->mask_base);\n    h->mask_base = h->mask = nullptr;", "    cudaFree(h->mask_base);\n    cudaFree(h->shadow_base);\n    cudaFree(h->bits);\n    h->mask_base = h->mask = nullptr;", "host: switching the masks off frees the shadows (the defect the device-lattice mode found)"),
     ("spk_cuda.cu", "ev.thr[dE] = t > 4294967295.0 ? 4294967295u : (uint32_t)t;", "ev.thr[dE] = t > 4294967295.0 ? 4294967295u : (uint32_t)t + 1u;", "host: acceptance thresholds one too high"),
 ]
 
