@@ -60,7 +60,9 @@ def draw_case(rng, max_sites):
     return {"lat": lat, "model": model, "n": [nx, ny, nz], "q": q, "T": T, "tier": tier, "mode": mode,
             "nsweeps": int(rng.integers(1, 4)), "nloop": int(rng.choice([1, 1, 1, 2, 3])),
             "nsector": int(rng.choice([2, 4, 8]) if dim3 else rng.choice([2, 4])), "seed": int(rng.integers(1, 2**40)),
-            "start": str(rng.choice(["random", "random", "grains", "few"])), "sweep0": int(rng.integers(0, 1000))}
+            "start": str(rng.choice(["random", "random", "grains", "few"])), "sweep0": int(rng.integers(0, 1000)),
+            # shape of the persistent launches: multi-step work items / several items per CTA (model_entry.cuh)
+            "chunks": int(rng.choice([0, 0, 1, 2])), "ctas": int(rng.choice([0, 0, 1, 3]))}
 
 
 def run_case(c):
@@ -71,6 +73,10 @@ def run_case(c):
     for k in [k for k in os.environ if k.startswith("SPK_CUDA_") and k not in ("SPK_CUDA_LIB", "SPK_CUDA_ALLOW_EMULATOR")]:
         del os.environ[k]
     os.environ.update(TIERS[c["tier"]])
+    if c.get("chunks"):
+        os.environ["SPK_CUDA_MAX_PLANE_CHUNKS"] = str(c["chunks"])
+    if c.get("ctas"):
+        os.environ["SPK_CUDA_MAX_CTAS"] = str(c["ctas"])
     model, lat, n, q, T = c["model"], c["lat"], c["n"], c["q"], c["T"]
     o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
     rng = np.random.default_rng(c["seed"])

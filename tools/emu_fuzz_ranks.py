@@ -58,7 +58,8 @@ def draw_case(rng, world):
             "between": [str(x) for x in rng.choice(["none", "energy", "clusters", "download"], size=3)],
             "start": str(rng.choice(["random", "few", "grains"])),
             # potts/pin: half of the cases get their pins from the device-side `pin f 0 0` (collective) instead of the upload
-            "pin": float(rng.choice([0.0, 0.0, 0.02, 0.3]))}
+            "pin": float(rng.choice([0.0, 0.0, 0.02, 0.3])),
+            "chunks": int(rng.choice([0, 0, 1, 2])), "ctas": int(rng.choice([0, 0, 1, 3]))}
 
 
 def worker(cases):
@@ -76,6 +77,10 @@ def worker(cases):
         os.environ.update(TIERS[c["tier"]])
         if c["halo"] == "nccl":
             os.environ["SPK_CUDA_NO_P2P"] = "1"
+        if c.get("chunks"):
+            os.environ["SPK_CUDA_MAX_PLANE_CHUNKS"] = str(c["chunks"])
+        if c.get("ctas"):
+            os.environ["SPK_CUDA_MAX_CTAS"] = str(c["ctas"])
         model, lat, n, q, T = c["model"], c["lat"], c["n"], c["q"], c["T"]
         o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
         rng = np.random.default_rng(c["seed"])
