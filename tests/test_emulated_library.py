@@ -234,6 +234,15 @@ def test_random_cases_on_one_rank(emu_lib):
     assert r.returncode == 0 and "80 / 80 cases, 0 failures" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_random_call_sequences_on_one_handle(emu_lib):
+    """tools/emu_fuzz_api.py: random ORDER of ABI calls on one handle (sweeps, colour sets, injected / strict sweeps,
+    uploads, energies, clusters, temperature / seed changes, masks on / off, set site range, pins, randomize, ...),
+    device == oracle after every call: the library's copies of the lattice stay consistent across entry points"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emu_fuzz_api.py"), "--cases", "20", "--ops", "16", "--seed", "5"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "20 / 20 sequences, 0 failures" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 TIER_SCRIPT = r"""
 import ctypes as C, json, os, sys
 import numpy as np
