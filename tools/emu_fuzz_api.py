@@ -234,6 +234,206 @@ def run_case(c):
     return None
 
 
+def run_case_ranks(c, dist, rank, world, local):
+    """the same idea on several ranks (one process each): every call is made collectively, rank 0 compares the gathered
+    slabs with the oracle after every step"""
+    import numpy as np
+    import torch
+    import oracle_py as O
+    from spparks_b200 import LatticeSweep
+    keep = ("SPK_CUDA_LIB", "SPK_CUDA_ALLOW_EMULATOR", "SPK_CUDA_NCCL_LIB")
+    for k in [k for k in os.environ if k.startswith("SPK_CUDA_") and k not in keep]:
+        del os.environ[k]
+    os.environ.update(TIER_ENV[c["tier"]])
+    if c.get("halo") == "nccl":
+        os.environ["SPK_CUDA_NO_P2P"] = "1"
+    model, lat, q = c["model"], c["lat"], c["q"]
+    n = list(c["n"])
+    dim3 = lat.startswith("sc")
+    per = max(2 if dim3 else 4, (n[2] if dim3 else n[1]) // 2 * 2)  # even slab thickness (2-D: >= the 4 ghost rows)
+    if dim3:
+        n[2] = per * world
+    else:
+        n[1] = per * world
+    T, seed = c["T"], c["seed"]
+    top = 2 if model.startswith("ising") else q
+    o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
+    colors = o.colors()
+    want = np.random.default_rng(seed).integers(1, top + 1, size=o.nsites, dtype=np.int32)
+    s = LatticeSweep(model, lat, n[0], n[1], n[2], nspins=q, temperature=T, seed=seed, device=local, rank=rank, nranks=world)
+    idt = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(LatticeSweep.comm_id()), dtype=torch.uint8)
+    dist.broadcast(idt, 0)
+    s.comm_init(idt.numpy().tobytes())
+    lo, hi = rank * s.nlocal, (rank + 1) * s.nlocal
+    s.upload(want[lo:hi])
+    mask = None
+    nacc = natt = 0
+    sweep = 100
+    siteseeds = None
+
+    def gather(arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return torch.cat(parts).numpy()
+
+    def total(vals):
+        t = torch.tensor(vals, dtype=torch.float64)
+        dist.all_reduce(t)
+        return [float(x) for x in t]
+
+    def check(what):
+        got = gather(s.download())
+        cnt = total(list(s.counters()))
+        if rank != 0:
+            return None
+        if not np.array_equal(got, want):
+            bad = np.flatnonzero(got != want)
+            return "%s: spins differ at %d sites, first %d" % (what, bad.size, int(bad[0]))
+        # (mask bytes are not compared here: a change unmasks its neighbours in the rank's OWN arrays, ghost copies
+        # included, in the reference too, so the bytes next to a slab boundary depend on the decomposition; without
+        # sectors every colour set is unmasked before it is swept, so the spins do not)
+        if (int(cnt[0]), int(cnt[1])) != (nacc, natt):
+            return "%s: counters %r, expected %r" % (what, (int(cnt[0]), int(cnt[1])), (nacc, natt))
+        return None
+
+    verdict = None
+    for step, opd in enumerate(c["ops"]):
+        op, a, b, u = opd["op"], opd["a"], opd["b"], opd["u"]
+        tag = "step %d %s" % (step, op)
+        bad = None
+        if op == "sweeps":
+            k = 1 + a % 3
+            if mask is None:
+                for i in range(k):
+                    nacc += o.sweep_philox(want, seed, sweep + i)
+            else:
+                for i in range(k):
+                    for col in range(1, o.ncolors + 1):
+                        mask[colors == col] = 0
+                        nacc += o.halfsweep_philox_mask(want, mask, seed, sweep + i, col, 0, None)
+            natt += k * o.nsites
+            s.sweeps(sweep, k)
+            sweep += k
+        elif op == "color":
+            col, nloop = 1 + a % o.ncolors, 1 + b % 3
+            s.halo_exchange()  # comm->all() before the set, as the plugin does (src/app_lattice.cpp:648-652)
+            if mask is None:
+                for l in range(nloop):
+                    nacc += o.halfsweep_philox(want, seed, sweep, col, iloop=l)
+                natt += nloop * int((colors == col).sum())
+                s.sweep_color(sweep, col, None, nloop)
+            else:
+                mask[colors == col] = 0
+                s.mask_clear_border(None, col)
+                nacc += o.halfsweep_philox_mask(want, mask, seed, sweep, col, 0, None)
+                natt += int((colors == col).sum())
+                s.sweep_color(sweep, col, None, 1)
+            sweep += 1
+        elif op == "injected" and mask is None:
+            col = 1 + a % o.ncolors
+            kk = np.random.default_rng(a).integers(1, O.IM - 1, size=o.nsites, dtype=np.int32)
+            u1, u2 = O.injected_uniforms(kk)
+            nacc += o.halfsweep_injected(want, col, u1, u2)
+            natt += int((colors == col).sum())
+            s.halo_exchange()
+            s.sweep_color_injected(col, u1[lo:hi], u2[lo:hi])
+        elif op == "strict" and mask is None:
+            if siteseeds is None:
+                siteseeds = o.strict_siteseeds(O.mars(1 + a % 900000000))
+                s.set_siteseeds(siteseeds[lo:hi])
+            nacc += o.sweeps_strict(want, siteseeds, 1)
+            natt += o.nsites
+            for col in range(1, o.ncolors + 1):
+                s.halo_exchange()
+                s.sweep_color_strict(col, None, 1)
+            if not np.array_equal(gather(s.get_siteseeds()), siteseeds) and rank == 0:
+                bad = tag + ": site seeds differ"
+        elif op == "upload":
+            want = np.random.default_rng(a).integers(1, top + 1, size=o.nsites, dtype=np.int32)
+            if model == "potts/pin" and u < 0.5:
+                want[np.random.default_rng(b).random(o.nsites) < 0.1] = q + 1
+            s.upload(want[lo:hi])
+        elif op == "energy":
+            e = total([s.energy()])[0]
+            if rank == 0 and e != o.total_energy(want):
+                bad = tag + ": energy differs"
+        elif op == "site_energy":
+            e = gather(s.site_energy())
+            if rank == 0 and int(e.sum()) != int(o.total_energy(want)):
+                bad = tag + ": per-site energies do not add up to the total"
+        elif op == "clusters":
+            got = s.cluster_stats()
+            if rank == 0:
+                oc = o.clusters(want)
+                if got[0] != oc[0] or abs(got[1] - oc[1]) > 1e-9 * oc[1] or abs(got[2] - oc[2]) > 1e-9 * oc[2]:
+                    bad = tag + ": cluster statistics %r, oracle %r" % (got, oc[:3])
+        elif op == "temperature":
+            T = [0.0, 0.3, 0.9, 2.0][a % 4]
+            o = O.Oracle(model, lat, n[0], n[1], n[2], q, T)
+            s.set_temperature(T)
+        elif op == "seed":
+            seed = 1 + (a * 7919 + b) % (2**40)
+            s.set_seed(seed)
+        elif op == "mask_on":
+            mask = np.zeros(o.nsites, dtype=np.uint8)
+            s.mask_enable(True)
+        elif op == "mask_off":
+            mask = None
+            s.mask_enable(False)
+        elif op == "set_range":
+            park = 1 + a % (O.IM - 2)
+            vlo = 1 + b % top
+            vhi = vlo + (a % (top - vlo + 1))
+            state, am = park, 1.0 / O.IM
+            vals = np.empty(o.nsites, dtype=np.int32)
+            for i in range(o.nsites):
+                state = state * 16807 % O.IM
+                vals[i] = vlo + min(int(state * am * (vhi - vlo + 1)), vhi - vlo)
+            want = vals
+            s.set_site_range(park, vlo, vhi)
+        elif op == "pin" and model == "potts/pin":
+            m = O.mars(1 + a % 900000000)
+            park = int(O.lib().orc_mars_uniform(O.C.byref(m)) * O.IM) or 1
+            frac = [0.02, 0.1, 0.3][b % 3]
+            if int((want > q).sum()) <= int(frac * o.nsites) + o.nsites // 2:
+                o.pin_create(want, frac, 0, 0, O.mars(1 + a % 900000000))
+                s.pin_create(park, frac)
+        elif op == "randomize":
+            s.randomize(a, 1, top)
+            want = gather(s.download()).copy()
+        elif op == "reset_counters":
+            s.reset_counters()
+            nacc = natt = 0
+        else:
+            continue
+        bad = bad or check(tag)
+        flag = torch.tensor([1 if bad else 0], dtype=torch.int32)
+        dist.all_reduce(flag)
+        if int(flag.item()):
+            verdict = bad or "failed on rank 0"
+            break
+    s.close()
+    return verdict
+
+
+def worker_ranks(cases):
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dist.init_process_group("gloo")
+    for c in cases:
+        try:
+            r = run_case_ranks(c, dist, rank, world, local)
+        except Exception as e:  # noqa: BLE001
+            r = "exception on rank %d: %r" % (rank, e)
+            print("FUZZ_NOTE " + r, flush=True)
+        if rank == 0:
+            print(("FUZZ_OK" if r is None else "FUZZ_FAIL " + json.dumps({"case": c, "what": r})), flush=True)
+    dist.destroy_process_group()
+
+
 def child(cases):
     for c in cases:
         try:
@@ -250,9 +450,15 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--batch", type=int, default=20)
     ap.add_argument("--child", default=None)
+    ap.add_argument("--ranks", type=int, default=1)
+    ap.add_argument("--port", type=int, default=29761)
+    ap.add_argument("--worker-ranks", default=None)
     args = ap.parse_args()
     if args.child:
         child(json.loads(open(args.child).read()))
+        return 0
+    if args.worker_ranks:
+        worker_ranks(json.loads(open(args.worker_ranks).read()))
         return 0
     import importlib.util
     import tempfile
@@ -264,6 +470,33 @@ def main():
     env = dict(os.environ, SPK_CUDA_LIB=lib, SPK_CUDA_ALLOW_EMULATOR="1")
     rng = np.random.default_rng(args.seed)
     cases = [draw_case(rng, args.ops) for _ in range(args.cases)]
+    if args.ranks > 1:
+        for c in cases:
+            c["halo"] = str(rng.choice(["p2p", "p2p", "nccl"]))
+        arena = tempfile.mkdtemp(prefix="spk_emu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            cfile = os.path.join(arena, "cases.json")
+            json.dump(cases, open(cfile, "w"))
+            env.update(SPK_CUDA_NCCL_LIB=be.NCCL_LIB, SPK_EMU_ARENA_DIR=arena, SPK_EMU_WORKERS="2", OMP_NUM_THREADS="1")
+            r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.ranks), "--master-addr",
+                                "127.0.0.1", "--master-port", str(args.port), os.path.abspath(__file__), "--worker-ranks", cfile],
+                               env=env, cwd=ROOT, capture_output=True, text=True)
+        finally:
+            import shutil
+            shutil.rmtree(arena, ignore_errors=True)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("FUZZ_OK") or l.startswith("FUZZ_FAIL")]
+        fails = [json.loads(l[10:]) for l in lines if l.startswith("FUZZ_FAIL")]
+        print("%d ranks: %d / %d sequences ok" % (args.ranks, len(lines) - len(fails), len(cases)))
+        for f in fails[:10]:
+            print("FAIL", f["what"], "|", f["case"]["model"], f["case"]["lat"], f["case"]["n"], "q", f["case"]["q"], f["case"]["tier"], f["case"]["halo"],
+                  "|", " ".join(o["op"] for o in f["case"]["ops"]))
+        for l in r.stdout.splitlines():
+            if l.startswith("FUZZ_NOTE"):
+                print(l)
+        if len(lines) != len(cases):
+            print("the run ended early:\n" + r.stdout[-1000:] + r.stderr[-3000:])
+            return 1
+        return 1 if fails else 0
     fails, done = [], 0
     with tempfile.TemporaryDirectory() as tmp:
         for bnum in range(0, len(cases), args.batch):
