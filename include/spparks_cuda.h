@@ -141,6 +141,9 @@ int spk_cuda_sweep_color_strict(spk_cuda_handle *h, int color, const int32_t *bo
 int spk_cuda_mask_enable(spk_cuda_handle *h, int on);
 int spk_cuda_mask_clear_border(spk_cuda_handle *h, const int32_t *box, int color);
 int spk_cuda_download_mask(spk_cuda_handle *h, unsigned char *host, int64_t n);
+/* the way back: the reference keeps its mask array from run to run (created and zeroed once,
+ * src/app_lattice.cpp:258-267), so a plugin that builds a new device lattice per run carries the bytes over */
+int spk_cuda_upload_mask(spk_cuda_handle *h, const unsigned char *host, int64_t n);
 
 /* nsweeps full sweeps of iterate_rejection with `sweep color`, `sector no`
  * (src/app_lattice.cpp:646-705): for each sweep, for each colour 1..ncolors: ghost refresh

@@ -74,6 +74,7 @@ class AppCudaMixin : public Base, public SpkCudaHost {
     device_current = 0;
     device_only = 0;
     dev_nloop = 1;
+    masks_on = 0;
   }
 
   virtual ~AppCudaMixin()
@@ -288,7 +289,9 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       }
       check(spk_cuda_set_seed(handle,seed));
       check(spk_cuda_set_temperature(handle,this->temperature));
-      check(spk_cuda_mask_enable(handle,this->Lmask ? 1 : 0));
+      if (!this->Lmask) check(spk_cuda_mask_enable(handle,0));
+      else if (!masks_on) check(spk_cuda_mask_enable(handle,1));   // once: the masks live on from run to run (:258-267)
+      masks_on = this->Lmask ? 1 : 0;
       // init_app's spin check (src/app_potts.cpp:83-90), where the spins are
       if (spk_cuda_validate_spins(handle) != 0) this->error->one(FLERR,"One or more sites have invalid values");
       return;
@@ -300,12 +303,24 @@ class AppCudaMixin : public Base, public SpkCudaHost {
       seed_set = 1;
     }
 
+    // the reference creates and zeroes its mask array once and keeps it from run to run
+    // (src/app_lattice.cpp:258-267): the bytes of the previous run's device lattice are carried over
+    unsigned char *saved_mask = NULL;
+    if (handle && this->Lmask && masks_on && this->nlocal > 0) {
+      saved_mask = new unsigned char[this->nlocal];
+      if (spk_cuda_download_mask(handle,saved_mask,this->nlocal)) { delete [] saved_mask; saved_mask = NULL; }
+    }
     if (handle) { spk_cuda_destroy(handle); handle = NULL; }
 
     spk_cuda_desc desc;
     fill_desc(desc,this->temperature);
     check(spk_cuda_create(&desc,&handle));
-    if (this->Lmask) check(spk_cuda_mask_enable(handle,1));   // src/app_lattice.cpp:258-267
+    if (this->Lmask) {
+      check(spk_cuda_mask_enable(handle,1));
+      if (saved_mask) check(spk_cuda_upload_mask(handle,saved_mask,this->nlocal));
+    }
+    delete [] saved_mask;
+    masks_on = this->Lmask ? 1 : 0;
 
     // tri with an odd number of rows: the two basis sites of the middle row fall into different
     // sectors (y = (j+1/2)*sqrt(3) vs ymid, src/app_lattice.cpp:959-974): not a box of cells
@@ -457,6 +472,7 @@ class AppCudaMixin : public Base, public SpkCudaHost {
   int device,nspins_cuda,seed_set,warned,device_current,host_sync;
   int device_only;      // the lattice lives on the device only (cuda_create_sites): nlocal = 0 on the host
   int dev_nloop;        // its nloop (setup)
+  int masks_on;         // the device lattice carries mask bytes of an earlier run
   void *pinned;
   size_t pinned_bytes;
   double perf_sites,perf_seconds;

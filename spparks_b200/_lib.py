@@ -27,7 +27,7 @@ SYMBOLS = [
     "spk_cuda_cluster_ids", "spk_cuda_neigh_variant", "spk_cuda_timer_lap", "spk_cuda_timer_laps",
     "spk_cuda_digest", "spk_cuda_mask_enable", "spk_cuda_mask_clear_border", "spk_cuda_download_mask",
     "spk_cuda_host_register", "spk_cuda_host_unregister", "spk_cuda_set_site_range", "spk_cuda_site_energy",
-    "spk_cuda_sweep_path", "spk_cuda_pin_create", "spk_cuda_accept_thresholds", "spk_cuda_set_seed", "spk_cuda_validate_spins",
+    "spk_cuda_sweep_path", "spk_cuda_pin_create", "spk_cuda_accept_thresholds", "spk_cuda_set_seed", "spk_cuda_validate_spins", "spk_cuda_upload_mask",
 ]
 
 
@@ -100,6 +100,7 @@ def load():
     L.spk_cuda_mask_enable.argtypes = [vp, C.c_int]
     L.spk_cuda_mask_clear_border.argtypes = [vp, i32p, C.c_int]
     L.spk_cuda_download_mask.argtypes = [vp, vp, C.c_int64]
+    L.spk_cuda_upload_mask.argtypes = [vp, vp, C.c_int64]
     L.spk_cuda_host_register.argtypes = [vp, C.c_size_t]
     L.spk_cuda_host_unregister.argtypes = [vp]
     L.spk_cuda_set_site_range.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]

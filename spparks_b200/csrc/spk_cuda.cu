@@ -1262,6 +1262,16 @@ int spk_cuda_download_mask(spk_cuda_handle *h, unsigned char *host, int64_t n) {
   return 0;
 }
 
+int spk_cuda_upload_mask(spk_cuda_handle *h, const unsigned char *host, int64_t n) {
+  if (!h || !host) return fail("null argument");
+  if (!h->mask) return fail("masking is not enabled (spk_cuda_mask_enable)");
+  if (n != h->nlocal) return fail("upload of %lld mask bytes, slab owns %lld sites", (long long)n, (long long)h->nlocal);
+  CU(cudaSetDevice(h->d.device));
+  CU(cudaMemcpyAsync(h->mask, host, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int spk_cuda_digest(spk_cuda_handle *h, uint64_t *digest) {
   if (!h || !digest) return fail("null argument");
   CU(cudaSetDevice(h->d.device));

@@ -179,6 +179,11 @@ class LatticeSweep:
     def mask_clear_border(self, box=None, color=0):
         _lib.check(self.L.spk_cuda_mask_clear_border(self.h, _box(box), color))
 
+    def upload_mask(self, mask):
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert mask.size == self.nlocal
+        _lib.check(self.L.spk_cuda_upload_mask(self.h, mask.ctypes.data_as(C.c_void_p), self.nlocal))
+
     def download_mask(self):
         out = np.empty(self.nlocal, dtype=np.uint8)
         _lib.check(self.L.spk_cuda_download_mask(self.h, out.ctypes.data_as(C.c_void_p), self.nlocal))

@@ -132,7 +132,7 @@ def test_cluster_tests_pass_on_the_emulated_library(emu_lib):
 def test_device_lattice_scripts_pass_on_the_emulated_library(emu_lib):
     """`cuda_create_sites`: scripts whose lattice lives on the device only print the table of the same script
     with a host lattice (tests/test_zz_device_lattice.py)"""
-    assert _run_gpu_tests(emu_lib, ["tests/test_zz_device_lattice.py"]) >= 8
+    assert _run_gpu_tests(emu_lib, ["tests/test_zz_device_lattice.py"]) >= 10
 
 
 def test_more_parity_tests_pass_on_the_emulated_library(emu_lib):
