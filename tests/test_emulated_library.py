@@ -243,6 +243,114 @@ def test_random_call_sequences_on_one_handle(emu_lib):
     assert r.returncode == 0 and "20 / 20 sequences, 0 failures" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+# ---- several MPI ranks: the reference's own parallel code and the plugin's multi-rank path -------------------------
+SPK_CUDA_MPI = os.path.join(ROOT, "plugin", "_build", "spk_cuda_mpi")
+SPK_REF_MPI = os.path.join(ROOT, "plugin", "_build", "spk_ref_mpi")
+needs_mpi_emu = pytest.mark.skipif(not (os.path.exists(SPK_CUDA_MPI) and os.path.exists(SPK_REF_MPI)),
+                                   reason="plugin/_build/spk_*_mpi not built (make -C plugin mpi; needs the reference tree)")
+
+
+def _mpirun(nranks, binary, script, env):
+    """ranks = processes of this host (tests/host_shim/mpi/mpi_emu.cpp); returns rank 0's output"""
+    import shutil
+    import tempfile
+    work = tempfile.mkdtemp(prefix="spk_mpi_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        path = os.path.join(work, "in.script")
+        open(path, "w").write(script)
+        procs = []
+        for r in range(nranks):
+            e = dict(env, SPK_MPI_RANK=str(r), SPK_MPI_SIZE=str(nranks), SPK_MPI_DIR=work, SPK_EMU_ARENA_DIR=work, SPK_EMU_WORKERS="2")
+            procs.append(subprocess.Popen([binary, "-in", path, "-log", "none"], cwd=work, env=e, stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT, text=True))
+        outs = []
+        for p in procs:
+            try:
+                outs.append(p.communicate(timeout=600)[0])
+            except subprocess.TimeoutExpired:
+                p.kill()
+                outs.append(p.communicate()[0] + "\nTIMEOUT")
+        assert all(p.returncode == 0 for p in procs) and "ERROR" not in outs[0], "\n".join(o[-1500:] for o in outs)
+        return outs[0]
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def _plugin_helpers():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_plugin as P
+    return P
+
+
+@needs_mpi_emu
+def test_reference_on_several_ranks_through_the_mpi_emulation():
+    """the MPI emulation itself: the UNMODIFIED reference on 2 and 4 ranks prints the serial table of a
+    `sweep color/strict` script (create_sites, ghost communication, reductions: all through mpi_emu.cpp)"""
+    P = _plugin_helpers()
+    case = dict(P.STRICT_CASES[0])
+    script = P.STRICT.format(**dict(case, app="%s %d" % (case["app"], case["q"])))
+    serial = P.stats_rows(P.run(P.SPK_REF, script))
+    for n in (2, 4):
+        par = script.replace("create_box box", "processors 1 1 %d\ncreate_box box" % n)
+        assert P.stats_rows(_mpirun(n, SPK_REF_MPI, par, dict(os.environ))) == serial
+
+
+@needs_mpi_emu
+@pytest.mark.parametrize("icase,nranks", [(0, 2), (0, 4), (2, 2), (3, 2), (4, 2), (6, 2)])
+def test_plugin_on_several_mpi_ranks_prints_the_reference_table(emu_lib, icase, nranks):
+    """The /cuda app styles on more than one MPI rank (never executed before: the image has no MPI): slab check,
+    NCCL id broadcast, per-colour ghost refresh, per-slab site seeds, device energies reduced over the ranks.
+    `sweep color/strict` scripts print the serial reference's table row for row."""
+    P = _plugin_helpers()
+    case = dict(P.STRICT_CASES[icase])
+    if case["dim"] == 3:
+        case["zr"] = "0 16"     # slabs of an even number of planes on 2 and 4 ranks
+    else:
+        case["ny"] = 32         # 2-D slabs: an even number of rows, at least the 4 ghost rows
+    def script(style):
+        app = style if case["app"].startswith("ising") else "%s %d" % (style, case["q"])
+        return P.STRICT.format(**dict(case, app=app))
+    ref = P.stats_rows(P.run(P.SPK_REF, script(case["app"])))
+    grid = "1 1 %d" % nranks if case["dim"] == 3 else "1 %d 1" % nranks
+    par = script(case["app"] + "/cuda").replace("create_box box", "processors %s\ncreate_box box" % grid)
+    par = par.replace("diag_style energy", "diag_style energy/cuda")
+    mod = _build_emu()
+    env = dict(_env(emu_lib), SPK_CUDA_NCCL_LIB=mod.NCCL_LIB)
+    assert P.stats_rows(_mpirun(nranks, SPK_CUDA_MPI, par, env)) == ref and len(ref) >= 4
+
+
+@needs_mpi_emu
+@pytest.mark.parametrize("create", ["create_sites box", "cuda_create_sites"])
+def test_plugin_philox_run_on_two_ranks_equals_one_rank(emu_lib, create):
+    """production mode (`sweep color`, `sector no`): the random stream is keyed on the global site, so two ranks
+    print the table of one rank; with the host lattice and with the device-only lattice (cuda_set / cuda_pin
+    collective on the slabs, cluster statistics merged across the slab boundary)"""
+    P = _plugin_helpers()
+    script = """seed 56789
+app_style potts/pin/cuda 12
+dimension 3
+lattice sc/26n 1.0
+region box block 0 16 0 8 0 8
+{procs}create_box box
+{create}
+cuda_set site range 1 12
+cuda_pin 0.05 0 0
+sweep color
+sector no
+temperature 0.9
+diag_style energy/cuda
+diag_style cluster/cuda
+stats 0.25
+run 1.0
+run 0.5
+"""
+    mod = _build_emu()
+    env = dict(_env(emu_lib), SPK_CUDA_NCCL_LIB=mod.NCCL_LIB)
+    one = P.stats_rows(_mpirun(1, SPK_CUDA_MPI, script.format(procs="", create=create), env))
+    two = P.stats_rows(_mpirun(2, SPK_CUDA_MPI, script.format(procs="processors 1 1 2\n", create=create), env))
+    assert len(one) >= 6 and two == one
+
+
 TIER_SCRIPT = r"""
 import ctypes as C, json, os, sys
 import numpy as np
