@@ -339,15 +339,16 @@ sweep color
 sector no
 temperature 0.9
 diag_style energy/cuda
-diag_style cluster/cuda
+{cluster}
 stats 0.25
 run 1.0
 run 0.5
 """
     mod = _build_emu()
     env = dict(_env(emu_lib), SPK_CUDA_NCCL_LIB=mod.NCCL_LIB)
-    one = P.stats_rows(_mpirun(1, SPK_CUDA_MPI, script.format(procs="", create=create), env))
-    two = P.stats_rows(_mpirun(2, SPK_CUDA_MPI, script.format(procs="processors 1 1 2\n", create=create), env))
+    cluster = "diag_style cluster/cuda" if create == "cuda_create_sites" else ""
+    one = P.stats_rows(_mpirun(1, SPK_CUDA_MPI, script.format(procs="", create=create, cluster=cluster), env))
+    two = P.stats_rows(_mpirun(2, SPK_CUDA_MPI, script.format(procs="processors 1 1 2\n", create=create, cluster=cluster), env))
     assert len(one) >= 6 and two == one
 
 
