@@ -9,6 +9,7 @@
 //   @save <file>              app->iarray[0] -> raw int32[nlocal]
 //   @neigh <file>             int32 header {nlocal,maxneigh}, then neighbor[i][0..maxneigh) (local idx)
 //   @colors <file>            int32[nlocal]: Lattice::id2color(id[i],1)   (src/lattice.cpp:234)
+//   @ids <file>               int32[nlocal]: global ids of the owned sites, local order
 //   @sets <file>              int32 nset, then per set {nlocal, site2i[...]}  (src/app_lattice.cpp:954)
 //   @siteseeds <file>         int32[nlocal] per-site Park-Miller seeds of sweep color/strict
 //   @halfsweep <color> <kfile>
@@ -142,6 +143,10 @@ int main(int argc, char **argv) {
     } else if (!strcmp(cmd, "@colors")) {
       std::vector<int> v(nlocal);
       for (int i = 0; i < nlocal; i++) v[i] = spk->domain->lattice->id2color(al->id[i], 1);
+      write_ints(s1, v.data(), nlocal);
+    } else if (!strcmp(cmd, "@ids")) {   // int32[nlocal]: global site ids of the owned sites (several ranks: this rank's)
+      std::vector<int> v(nlocal);
+      for (int i = 0; i < nlocal; i++) v[i] = (int)al->id[i];
       write_ints(s1, v.data(), nlocal);
     } else if (!strcmp(cmd, "@sets")) {
       Peek::Set *set = peek(al, &Peek::set);

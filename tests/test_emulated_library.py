@@ -250,7 +250,7 @@ needs_mpi_emu = pytest.mark.skipif(not (os.path.exists(SPK_CUDA_MPI) and os.path
                                    reason="plugin/_build/spk_*_mpi not built (make -C plugin mpi; needs the reference tree)")
 
 
-def _mpirun(nranks, binary, script, env):
+def _mpirun(nranks, binary, script, env, keep=None):
     """ranks = processes of this host (tests/host_shim/mpi/mpi_emu.cpp); returns rank 0's output"""
     import shutil
     import tempfile
@@ -261,8 +261,13 @@ def _mpirun(nranks, binary, script, env):
         procs = []
         for r in range(nranks):
             e = dict(env, SPK_MPI_RANK=str(r), SPK_MPI_SIZE=str(nranks), SPK_MPI_DIR=work, SPK_EMU_ARENA_DIR=work, SPK_EMU_WORKERS="2")
-            procs.append(subprocess.Popen([binary, "-in", path, "-log", "none"], cwd=work, env=e, stdout=subprocess.PIPE,
-                                          stderr=subprocess.STDOUT, text=True))
+            cwd = work
+            if keep is not None:  # every rank in its own directory, kept for the caller
+                cwd = os.path.join(keep, "rank%d" % r)
+                os.makedirs(cwd)
+                e["SPK_TRACE_SETS"] = os.path.join(cwd, "sets.trace")
+            args = [binary, "-in", path, "-log", "none"] if not binary.endswith("ref_driver_mpi") else [binary, path, "-quiet"]
+            procs.append(subprocess.Popen(args, cwd=cwd, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
         outs = []
         for p in procs:
             try:
@@ -350,6 +355,60 @@ run 0.5
     one = P.stats_rows(_mpirun(1, SPK_CUDA_MPI, script.format(procs="", create=create, cluster=cluster), env))
     two = P.stats_rows(_mpirun(2, SPK_CUDA_MPI, script.format(procs="processors 1 1 2\n", create=create, cluster=cluster), env))
     assert len(one) >= 6 and two == one
+
+
+@needs_mpi_emu
+@pytest.mark.parametrize("lat,dim,n,procs,sector", [
+    # (with slabs of the last dimension the reference only admits 8 sectors in 3-D and 4 in 2-D, src/app_lattice.cpp:168-185)
+    ("sc/26n", 3, (8, 8, 16), "1 1 2", "yes"), ("sc/26n", 3, (8, 12, 16), "1 1 4", "8"), ("sc/6n", 3, (6, 6, 8), "1 1 2", "yes"),
+    ("sq/4n", 2, (12, 16, 1), "1 2 1", "yes"), ("sq/8n", 2, (8, 24, 1), "1 3 1", "4"), ("tri", 2, (8, 16, 1), "1 2 1", "yes"),
+], ids=lambda v: str(v).replace(" ", ""))
+def test_plugin_sector_boxes_equal_the_reference_sets_on_every_rank(emu_lib, tmp_path, lat, dim, n, procs, sector):
+    """`sweep color` + `sector yes|N` on several ranks: the reference cuts every rank's OWN sub-domain at its midpoints
+    (create_set, src/app_lattice.cpp:954-1026).  The loop sets the plugin hands to the library (logged by an
+    LD_PRELOAD interposer on spk_cuda_sweep_color) hold, rank by rank and in the reference's order, exactly the sites
+    of the reference's own sets (ref_driver @sets / @ids on the same ranks)."""
+    if not os.path.exists(os.path.join(ROOT, "plugin", "_build", "ref_driver_mpi")):
+        pytest.skip("plugin/_build/ref_driver_mpi not built")
+    mod = _build_emu()
+    trace_lib = os.path.join(mod.BUILD, "libtrace_sets.so")
+    subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", os.path.join(ROOT, "tests", "host_shim", "trace", "trace_sets.c"), "-o", trace_lib, "-ldl"])
+    nranks = int(procs.split()[dim - 1])
+    zr = "0 %d" % n[2] if dim == 3 else "-0.5 0.5"
+    head = ("seed 4711\napp_style %s\ndimension %d\nlattice %s 1.0\nregion box block 0 %d 0 %d %s\nprocessors %s\ncreate_box box\n"
+            "create_sites box\nset site range 1 5\nsweep color\nsector %s\ntemperature 0.5\n")
+    ref_dir, gpu_dir = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    os.makedirs(ref_dir)
+    os.makedirs(gpu_dir)
+    _mpirun(nranks, os.path.join(ROOT, "plugin", "_build", "ref_driver_mpi"),
+            head % ("potts 5", dim, lat, n[0], n[1], zr, procs, sector) + "run 0.0\n@ids ids.bin\n@sets sets.bin\n", dict(os.environ), keep=ref_dir)
+    P = _plugin_helpers()
+    dt = 1.0 / 5
+    env = dict(_env(emu_lib), SPK_CUDA_NCCL_LIB=mod.NCCL_LIB, LD_PRELOAD=trace_lib)
+    _mpirun(nranks, SPK_CUDA_MPI, head % ("potts/cuda 5", dim, lat, n[0], n[1], zr, procs, sector) + "run %g\n" % (0.5 * dt), env, keep=gpu_dir)
+    nb = 2 if lat == "tri" else 1
+    o = __import__("oracle_py").Oracle("potts", lat, n[0], n[1], n[2], 5, 0.5)
+    colors = o.colors()
+    cell = np.arange(o.nsites) // nb
+    ci, cj, ck = cell % n[0], (cell // n[0]) % n[1], cell // (n[0] * n[1])
+    for r in range(nranks):
+        ids = np.fromfile(os.path.join(ref_dir, "rank%d" % r, "ids.bin"), dtype=np.int32)
+        raw = np.fromfile(os.path.join(ref_dir, "rank%d" % r, "sets.bin"), dtype=np.int32)
+        nset, nsector, ncolors = int(raw[0]), int(raw[1]), int(raw[2])
+        sets, pos = [], 3
+        for _ in range(nset):
+            cnt = int(raw[pos])
+            sets.append(np.sort(ids[raw[pos + 1:pos + 1 + cnt]] - 1))
+            pos += 1 + cnt
+        assert nset == nsector + nsector * ncolors and nsector > 1
+        calls = [tuple(int(x) for x in line.split()) for line in open(os.path.join(gpu_dir, "rank%d" % r, "sets.trace"))]
+        assert len(calls) == nsector * ncolors   # one sweep: every (sector, colour) set once, sector-major
+        for k, (sweep, color, nloop, ilo, ihi, jlo, jhi, klo, khi) in enumerate(calls):
+            isec, ic = divmod(k, ncolors)
+            assert color == ic + 1 and nloop == 1
+            inbox = (ci >= ilo) & (ci < ihi) & (cj >= jlo) & (cj < jhi) & (ck >= klo) & (ck < khi)
+            mine = np.flatnonzero(inbox & (colors == color))
+            assert np.array_equal(mine, sets[nsector + isec * ncolors + ic]), (r, isec, ic)
 
 
 TIER_SCRIPT = r"""
